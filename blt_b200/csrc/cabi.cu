@@ -1,0 +1,421 @@
+// cabi.cu -- the extern "C" surface of libblt_cuda.so (include/blt_cuda.h): contexts, strategies,
+// the per-chunk / pipelined / device-resident entry points.  No CPU compute path exists here: every
+// tokenizing call ends in a kernel launch from kernels.cu or fails.
+#include "../../include/blt_cuda.h"
+#include "host_config.h"
+#include "kernels.cuh"
+#include "pipeline.h"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define BLT_VERSION_STRING "0.2.2"  // CARGO_PKG_VERSION of the reference this build mirrors
+
+namespace bltc {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return bltc::fail(e__ == cudaErrorMemoryAllocation ? BLT_ERR_NOMEM : BLT_ERR_CUDA,     \
+                              std::string(#expr) + ": " + cudaGetErrorString(e__));                \
+    } while (0)
+
+// ---- Workspace: device scratch for one in-flight tokenization -------------------------------------
+int Workspace::ensure_scratch(size_t n_elems) {
+    if (n_elems <= scratch_elems && d_scratch) return BLT_OK;
+    if (d_scratch) cudaFree(d_scratch);
+    d_scratch = nullptr;
+    scratch_elems = 0;
+    const size_t want = std::max<size_t>(n_elems, 1u << 20);
+    CUDA_TRY(cudaMalloc(&d_scratch, bltk::sweep_scratch_bytes(want)));
+    scratch_elems = want;
+    scratch = bltk::sweep_scratch_carve(d_scratch, want);
+    return BLT_OK;
+}
+int Workspace::ensure_work(size_t chunk_bytes) {
+    if (!h_ctrl) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_ctrl), 64, cudaHostAllocDefault));
+    if (chunk_bytes <= work_chunk) return BLT_OK;
+    for (auto &p : d_work) { if (p) cudaFree(p); p = nullptr; }
+    if (d_align) cudaFree(d_align);
+    d_align = nullptr;
+    work_chunk = 0;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_work[0]), 2 * chunk_bytes + 64));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_work[1]), 2 * chunk_bytes + 64));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_align), chunk_bytes + 64));
+    work_chunk = chunk_bytes;
+    return BLT_OK;
+}
+void Workspace::release() {
+    if (d_scratch) cudaFree(d_scratch);
+    for (auto &p : d_work) if (p) cudaFree(p);
+    if (d_align) cudaFree(d_align);
+    if (h_ctrl) cudaFreeHost(h_ctrl);
+    d_scratch = nullptr; d_work[0] = d_work[1] = nullptr; d_align = nullptr; h_ctrl = nullptr;
+    scratch_elems = 0; work_chunk = 0;
+}
+
+// ---- run_device: enqueue the tokenization of a device buffer --------------------------------------
+// Fixed-ratio strategies and the single-sweep byte-pair path are fully asynchronous; the general
+// multi-sweep path synchronises `stream` once per sweep (it must read the "merged anything" flag).
+int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, size_t chunk, uint8_t *d_out,
+               size_t out_cap, uint64_t *d_chunk_ends, cudaStream_t stream, DeviceResult *res) {
+    res->kind = DeviceResult::KNOWN;
+    res->len = 0;
+    res->sweeps = 0;
+    if (n == 0) return BLT_OK;
+    if (chunk == 0 || chunk > n) chunk = n;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
+        return fail(BLT_ERR_INVALID_INPUT, "device buffers must be 16-byte aligned");
+    switch (s->mode) {
+        case Mode::Basic: {
+            if (out_cap < 2 * n) return fail(BLT_ERR_CAPACITY, "output capacity < 2*n");
+            CUDA_TRY(bltk::launch_widen(d_in, n, d_out, stream));
+            CUDA_TRY(bltk::launch_fill_chunk_ends(d_chunk_ends, n, chunk, 2, stream));
+            res->len = 2 * n;
+            res->launches = 1;
+            return BLT_OK;
+        }
+        case Mode::Passthrough: {
+            if (out_cap < n) return fail(BLT_ERR_CAPACITY, "output capacity < n");
+            CUDA_TRY(cudaMemcpyAsync(d_out, d_in, n, cudaMemcpyDeviceToDevice, stream));
+            CUDA_TRY(bltk::launch_fill_chunk_ends(d_chunk_ends, n, chunk, 1, stream));
+            res->len = n;
+            res->launches = 0;
+            return BLT_OK;
+        }
+        case Mode::BpePairs: {
+            int rc = ws.ensure_scratch(n);
+            if (rc) return rc;
+            bltk::SweepArgs a{};
+            a.in = d_in; a.n = n; a.chunk = chunk;
+            a.out = reinterpret_cast<uint16_t *>(d_out);
+            a.out_cap_tokens = out_cap / 2; a.out_base_tokens = 0;
+            a.chunk_ends = d_chunk_ends; a.chunk_ends_base = 0;
+            a.scratch = ws.scratch;
+            CUDA_TRY(bltk::launch_bpe_sweep_pairs(a, s->d_table, s->variant, stream));
+            res->kind = DeviceResult::IN_SCRATCH;
+            res->sweeps = 1;  // byte keys, ids >= 256: the reference's 2nd sweep cannot merge
+            res->launches = 1;
+            return BLT_OK;
+        }
+        case Mode::BpeGeneral: {
+            int rc = ws.ensure_scratch(chunk);
+            if (rc) return rc;
+            rc = ws.ensure_work(chunk);
+            if (rc) return rc;
+            const bltk::HashTableView view{s->d_slots, s->hash_mask, s->d_can_left, s->d_can_right};
+            const size_t n_chunks = (n + chunk - 1) / chunk;
+            std::vector<uint64_t> ends(n_chunks);
+            size_t out_bytes = 0;
+            uint32_t max_sweeps = 0;
+            res->launches = 0;
+            for (size_t k = 0; k < n_chunks; ++k) {
+                const size_t len = std::min(chunk, n - k * chunk);
+                const uint8_t *src = d_in + k * chunk;
+                if (reinterpret_cast<uintptr_t>(src) & 15u) {  // only when chunk is not a multiple of 16
+                    CUDA_TRY(cudaMemcpyAsync(ws.d_align, src, len, cudaMemcpyDeviceToDevice, stream));
+                    src = ws.d_align;
+                }
+                const void *cur = src;
+                size_t cur_n = len;
+                bool cur_u16 = false;
+                int which = 0;
+                uint32_t sweeps = 0;
+                for (;;) {  // the loop at tokenizer.rs:63-86, one launch per sweep
+                    bltk::SweepArgs a{};
+                    a.in = cur; a.n = cur_n; a.chunk = 0;
+                    a.out = reinterpret_cast<uint16_t *>(ws.d_work[which]);
+                    a.out_cap_tokens = chunk; a.out_base_tokens = 0;
+                    a.chunk_ends = nullptr; a.chunk_ends_base = 0;
+                    a.scratch = ws.scratch;
+                    CUDA_TRY(bltk::launch_bpe_sweep_hash(a, view, cur_u16, stream));
+                    CUDA_TRY(cudaMemcpyAsync(ws.h_ctrl, ws.scratch.ctrl, 32, cudaMemcpyDeviceToHost, stream));
+                    CUDA_TRY(cudaStreamSynchronize(stream));
+                    ++sweeps;
+                    ++res->launches;
+                    const uint64_t total = ws.h_ctrl[0];
+                    const uint32_t merged = reinterpret_cast<const uint32_t *>(ws.h_ctrl)[3];
+                    cur = ws.d_work[which];
+                    cur_n = size_t(total);
+                    cur_u16 = true;
+                    which ^= 1;
+                    if (!merged) break;  // tokenizer.rs:83-85
+                }
+                if (out_bytes + 2 * cur_n > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+                CUDA_TRY(cudaMemcpyAsync(d_out + out_bytes, cur, 2 * cur_n, cudaMemcpyDeviceToDevice, stream));
+                out_bytes += 2 * cur_n;
+                ends[k] = out_bytes;
+                max_sweeps = std::max(max_sweeps, sweeps);
+            }
+            if (d_chunk_ends) {
+                CUDA_TRY(cudaMemcpyAsync(d_chunk_ends, ends.data(), n_chunks * 8, cudaMemcpyHostToDevice, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));  // `ends` is a stack-owned host buffer
+            }
+            res->len = out_bytes;
+            res->sweeps = max_sweeps;
+            return BLT_OK;
+        }
+    }
+    return fail(BLT_ERR_INVALID_INPUT, "unknown strategy mode");
+}
+
+// Reads back the result of a K2 launch (after the caller synchronised the stream that ran it, or
+// by synchronising here).
+int finish_result(Workspace &ws, cudaStream_t stream, DeviceResult *res) {
+    if (res->kind != DeviceResult::IN_SCRATCH) return BLT_OK;
+    if (!ws.h_ctrl) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ws.h_ctrl), 64, cudaHostAllocDefault));
+    CUDA_TRY(cudaMemcpyAsync(ws.h_ctrl, ws.scratch.ctrl, 32, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return decode_ctrl(ws.h_ctrl, res);
+}
+int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res) {
+    const uint32_t overflow = reinterpret_cast<const uint32_t *>(h_ctrl)[4];
+    if (overflow) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+    res->len = size_t(h_ctrl[0]) * 2;
+    res->kind = DeviceResult::KNOWN;
+    return BLT_OK;
+}
+
+// ---- strategy construction ------------------------------------------------------------------------
+static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **out) {
+    auto s = std::unique_ptr<blt_strategy>(new blt_strategy());
+    s->ctx = ctx;
+    s->rules = std::move(rules);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    bool pairs_ok = true;
+    for (const auto &r : s->rules) pairs_ok = pairs_ok && r.left < 256 && r.right < 256 && r.value >= 256;
+    if (pairs_ok) {
+        // Every key is a byte pair and every id is >= 256 (always true for a merges.txt,
+        // config_loader.rs:27-40): one sweep is the fixpoint and the table is direct-indexed.
+        s->mode = Mode::BpePairs;
+        std::vector<uint16_t> tbl(bltk::kPairTableEntries);
+        for (uint32_t b0 = 0; b0 < 256; ++b0)
+            for (uint32_t b1 = 0; b1 < 256; ++b1) tbl[bltk::pair_table_index(b0, b1)] = uint16_t(b0 << 8);
+        for (const auto &r : s->rules)
+            tbl[bltk::pair_table_index(r.left, r.right)] = uint16_t((r.value >> 8) | (r.value << 8));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_table), tbl.size() * 2));
+        CUDA_TRY(cudaMemcpy(s->d_table, tbl.data(), tbl.size() * 2, cudaMemcpyHostToDevice));
+    } else {
+        s->mode = Mode::BpeGeneral;
+        size_t cap = 16;
+        while (cap < 2 * s->rules.size() + 2) cap <<= 1;
+        std::vector<bltk::HashSlot> slots(cap, bltk::HashSlot{0, 0, 0});
+        std::vector<uint32_t> cl(2048, 0), cr(2048, 0);
+        for (const auto &r : s->rules) {
+            const uint32_t key = (uint32_t(r.left) << 16) | r.right;
+            uint32_t h = bltk::hash_pair(key) & uint32_t(cap - 1);
+            while (slots[h].used) h = (h + 1) & uint32_t(cap - 1);
+            slots[h] = bltk::HashSlot{key, r.value, 1};
+            cl[r.left >> 5] |= 1u << (r.left & 31);
+            cr[r.right >> 5] |= 1u << (r.right & 31);
+        }
+        s->hash_mask = uint32_t(cap - 1);
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_slots), cap * sizeof(bltk::HashSlot)));
+        CUDA_TRY(cudaMemcpy(s->d_slots, slots.data(), cap * sizeof(bltk::HashSlot), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_can_left), 8192));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_can_right), 8192));
+        CUDA_TRY(cudaMemcpy(s->d_can_left, cl.data(), 8192, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_can_right, cr.data(), 8192, cudaMemcpyHostToDevice));
+    }
+    if (const char *v = getenv("BLT_SWEEP_VARIANT")) s->variant = atoi(v);
+    *out = s.release();
+    return BLT_OK;
+}
+
+}  // namespace bltc
+
+blt_strategy::~blt_strategy() {
+    if (ctx) cudaSetDevice(ctx->device);
+    if (d_table) cudaFree(d_table);
+    if (d_slots) cudaFree(d_slots);
+    if (d_can_left) cudaFree(d_can_left);
+    if (d_can_right) cudaFree(d_can_right);
+    resident.release();
+}
+
+using namespace bltc;
+
+extern "C" {
+
+const char *blt_version(void) { return BLT_VERSION_STRING; }
+const char *blt_last_error(void) { return g_last_error.c_str(); }
+
+int blt_device_count(int *count) {
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        if (count) *count = 0;
+        cudaGetLastError();
+        return fail(BLT_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    if (count) *count = n;
+    return BLT_OK;
+}
+
+int blt_ctx_create(int device, blt_ctx **out) {
+    if (!out) return fail(BLT_ERR_INVALID_INPUT, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    int rc = blt_device_count(&n);
+    if (rc) return rc;
+    if (device < 0 || device >= n) return fail(BLT_ERR_INVALID_INPUT, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(nullptr));  // force context creation so errors surface here
+    auto c = new blt_ctx();
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return BLT_OK;
+}
+
+void blt_ctx_destroy(blt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto &p : ctx->idle) p->release();
+    delete ctx;
+}
+
+int blt_strategy_basic(blt_ctx *ctx, blt_strategy **out) {
+    if (!ctx || !out) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    auto s = new blt_strategy();
+    s->ctx = ctx;
+    s->mode = Mode::Basic;
+    *out = s;
+    return BLT_OK;
+}
+
+int blt_strategy_passthrough(blt_ctx *ctx, blt_strategy **out) {
+    if (!ctx || !out) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    auto s = new blt_strategy();
+    s->ctx = ctx;
+    s->mode = Mode::Passthrough;
+    *out = s;
+    return BLT_OK;
+}
+
+int blt_strategy_bpe_from_file(blt_ctx *ctx, const char *merges_path, blt_strategy **out) {
+    if (!ctx || !out || !merges_path) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    *out = nullptr;
+    blth::MergeList rules;
+    const blth::Error e = blth::load_merges_file(merges_path, &rules);
+    if (e) return fail(BLT_ERR_INVALID_INPUT, "Failed to load BPE merges: " + e.msg);  // lib.rs:194-201
+    return build_strategy(ctx, std::move(rules), out);
+}
+
+int blt_strategy_bpe_from_pairs(blt_ctx *ctx, const uint16_t *left, const uint16_t *right, const uint16_t *value,
+                                size_t n, blt_strategy **out) {
+    if (!ctx || !out || (n && (!left || !right || !value))) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    *out = nullptr;
+    std::vector<blth::MergeRule> rules(n);
+    for (size_t i = 0; i < n; ++i) rules[i] = blth::MergeRule{left[i], right[i], value[i]};
+    return build_strategy(ctx, blth::dedup_rules(rules), out);
+}
+
+void blt_strategy_destroy(blt_strategy *s) { delete s; }
+
+size_t blt_strategy_num_merges(const blt_strategy *s) { return s ? s->rules.size() : 0; }
+
+int blt_process_chunk(blt_strategy *s, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_len) {
+    if (!s || !out_len || (n && (!in || !out))) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    *out_len = 0;
+    if (n == 0) return BLT_OK;  // tokenizer.rs:57-59, 109-111
+    return bltc::tokenize_host(s, in, n, n, BLT_CONTENT_NONE, out, out_cap, out_len);
+}
+
+int blt_tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk_size, int content_type, uint8_t *out,
+                      size_t out_cap, size_t *out_len) {
+    if (!s || !out_len || (n && !in) || !out) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    *out_len = 0;
+    return bltc::tokenize_host(s, in, n, chunk_size, content_type, out, out_cap, out_len);
+}
+
+int blt_process_resident(blt_strategy *s, const void *d_in, size_t n, size_t chunk_size, void *d_out, size_t out_cap,
+                         uint64_t *d_chunk_ends, void *stream, size_t *out_len) {
+    if (!s || (n && (!d_in || !d_out))) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->resident_mu);
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = run_device(s, s->resident, static_cast<const uint8_t *>(d_in), n, chunk_size, static_cast<uint8_t *>(d_out),
+                        out_cap, d_chunk_ends, st, &s->resident_result);
+    if (rc) return rc;
+    if (out_len) {
+        rc = finish_result(s->resident, st, &s->resident_result);
+        if (rc) return rc;
+        if (s->resident_result.kind == DeviceResult::KNOWN) CUDA_TRY(cudaStreamSynchronize(st));
+        *out_len = s->resident_result.len;
+    }
+    return BLT_OK;
+}
+
+int blt_resident_result(blt_strategy *s, void *stream, size_t *out_len, uint32_t *sweeps) {
+    if (!s) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->resident_mu);
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = finish_result(s->resident, st, &s->resident_result);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (out_len) *out_len = s->resident_result.len;
+    if (sweeps) *sweeps = s->resident_result.sweeps;
+    return BLT_OK;
+}
+
+// ---- host-only helpers ----------------------------------------------------------------------------
+int blt_load_bpe_merges(const char *path, uint16_t *left, uint16_t *right, uint16_t *value, size_t cap, size_t *n) {
+    if (!path || !n) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    blth::MergeList rules;
+    const blth::Error e = blth::load_merges_file(path, &rules);
+    if (e) return fail(e.code, e.msg);
+    *n = rules.size();
+    for (size_t i = 0; i < rules.size() && i < cap; ++i) {
+        if (left) left[i] = rules[i].left;
+        if (right) right[i] = rules[i].right;
+        if (value) value[i] = rules[i].value;
+    }
+    return BLT_OK;
+}
+
+int blt_parse_chunk_size(const char *s, size_t *out) {
+    if (!s || !out) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    const blth::Error e = blth::parse_chunk_size(s, out);
+    if (e) return fail(e.code, e.msg);
+    return BLT_OK;
+}
+
+size_t blt_effective_chunk_size(int has_cli, size_t cli_size, size_t threads, unsigned memcap, uint64_t total_ram_bytes) {
+    return blth::effective_chunk_size(has_cli != 0, cli_size, threads, memcap, total_ram_bytes);
+}
+
+size_t blt_determine_thread_count(int has_override, size_t override_val) {
+    return blth::determine_thread_count(has_override != 0, override_val);
+}
+
+uint16_t blt_content_type_token(int ct) {
+    switch (ct) {  // lib.rs:96-103
+        case BLT_CONTENT_TEXT: return 0xFF01;
+        case BLT_CONTENT_AUDIO: return 0xFF02;
+        case BLT_CONTENT_BIN: return 0xFF03;
+        case BLT_CONTENT_VIDEO: return 0xFF04;
+        default: return 0;
+    }
+}
+
+void blt_shard_chunks(size_t n_chunks, int n_gpus, size_t *bounds) {
+    if (n_gpus < 1) n_gpus = 1;
+    // chunk k -> GPU floor(k*G/K): GPU g owns [ceil(g*K/G), ceil((g+1)*K/G))
+    for (int g = 0; g <= n_gpus; ++g) bounds[g] = (size_t(g) * n_chunks + size_t(n_gpus) - 1) / size_t(n_gpus);
+}
+
+}  // extern "C"

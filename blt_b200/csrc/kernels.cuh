@@ -1,0 +1,92 @@
+// kernels.cuh -- launch interface of the sm_100a kernels behind libblt_cuda.so.
+//
+// K1  widen_kernel        BasicTokenizationStrategy::process_chunk  (blt_core/src/tokenizer.rs:108-123)
+// K2  bpe_sweep_kernel    one sweep of BpeStrategy::process_chunk   (blt_core/src/tokenizer.rs:63-86)
+//                         in its closed parallel form: pair lookup -> run parity ->
+//                         single-pass decoupled look-back -> compaction -> big-endian u16 store.
+// K3  the same sweep over u16 tokens with a general HashMap<(u16,u16),u16> (lib.rs:75).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace bltk {
+
+// Byte-pair table for K2: 65 536 u16 entries, direct-indexed by a swizzled (b0,b1) key.
+// entry = bswap16(id) when (b0,b1) is a rule (requires id >= 256, so the LOW byte of the stored
+// value is non-zero), else bswap16(b0) = b0 << 8 (low byte zero).  One shared-memory read therefore
+// yields membership AND the big-endian token to emit at that position.
+constexpr int kPairTableEntries = 65536;
+__host__ __device__ inline uint32_t pair_table_index(uint32_t b0, uint32_t b1) {
+    // Bank (= bits 1..5 of the u16 index) mixes both bytes so lanes holding the same frequent
+    // first byte with different second bytes do not collide.
+    const uint32_t x = b0 | (b1 << 8);
+    return x ^ ((x >> 7) & 0x3Eu);
+}
+
+// General map for K3: open addressing, linear probing, 8-byte slots.
+struct HashSlot {
+    uint32_t key;    // (left << 16) | right
+    uint16_t value;  // little-endian token id
+    uint16_t used;   // 1 if occupied
+};
+__host__ __device__ inline uint32_t hash_pair(uint32_t key) {
+    key ^= key >> 15; key *= 0x2c1b3c6du; key ^= key >> 12; key *= 0x297a2d39u; key ^= key >> 15;
+    return key;
+}
+struct HashTableView {
+    const HashSlot *slots;     // device
+    uint32_t mask;             // capacity - 1 (capacity is a power of two, load <= 0.5)
+    const uint32_t *can_left;  // device bitmap, 65 536 bits: token appears as a left component
+    const uint32_t *can_right; // device bitmap, 65 536 bits: token appears as a right component
+};
+
+// Per-launch scratch in device memory (zeroed by the launcher before every sweep).
+struct SweepScratch {
+    void *ctrl;              // start of the region: 64-byte control block, then the descriptors
+    uint64_t *total_tokens;  // ctrl+0 : number of tokens written by the sweep
+    uint32_t *tile_counter;  // ctrl+8 : dynamic tile id dispenser
+    uint32_t *merged_any;    // ctrl+12: set to 1 if any pair merged in this sweep
+    uint32_t *overflow;      // ctrl+16: set to 1 if the output capacity was exceeded
+    uint64_t *tile_status;   // ctrl+64: one word per tile (look-back descriptors)
+    size_t bytes;            // size of the whole region
+    size_t max_tiles;
+};
+size_t sweep_scratch_bytes(size_t n_elems_max);
+// Carves `mem` (device, >= sweep_scratch_bytes) into a SweepScratch.
+SweepScratch sweep_scratch_carve(void *mem, size_t n_elems_max);
+// Smallest tile (in input elements) any sweep configuration uses; sizes the status array.
+constexpr size_t kMinTileElems = 2048;
+
+struct SweepArgs {
+    const void *in;          // device, 16-byte aligned: u8 bytes (K2 / first K3 sweep) or BE u16 tokens
+    size_t n;                // number of input elements
+    size_t chunk;            // wall every `chunk` elements (0 = none besides the end)
+    uint16_t *out;           // device, 16-byte aligned, big-endian u16 tokens
+    size_t out_cap_tokens;   // capacity of out in tokens, counted from out[0]
+    size_t out_base_tokens;  // the first token of this sweep lands at out[out_base_tokens]
+    uint64_t *chunk_ends;    // optional device array: inclusive prefix of OUTPUT BYTES per chunk
+    size_t chunk_ends_base;  // bytes added to every chunk_ends entry (output before this launch)
+    SweepScratch scratch;
+};
+
+// K1.  16-byte loads, 32-byte stores.  n bytes in -> 2n bytes out (00 b pairs).
+cudaError_t launch_widen(const uint8_t *d_in, size_t n, uint8_t *d_out, cudaStream_t stream);
+// chunk_ends[k] = bytes_per_elem * min((k+1)*chunk, n) for the fixed-ratio strategies.
+cudaError_t launch_fill_chunk_ends(uint64_t *d_ends, size_t n, size_t chunk, unsigned bytes_per_elem,
+                                   cudaStream_t stream);
+// K2.  d_table = kPairTableEntries u16 in device memory (layout above).
+cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, int variant,
+                                   cudaStream_t stream);
+// K3.  in_is_u16: input is BE u16 tokens (true) or raw bytes (false).
+cudaError_t launch_bpe_sweep_hash(const SweepArgs &a, const HashTableView &t, bool in_is_u16,
+                                  cudaStream_t stream);
+// Number of kernels the launchers above enqueue per call (for bench.py's gpu_launches claim):
+// one memset node + one kernel.
+constexpr int kLaunchesPerSweep = 1;
+
+int num_sweep_variants();
+const char *sweep_variant_name(int variant);
+
+}  // namespace bltk

@@ -1,0 +1,95 @@
+// pipeline.h -- internal types shared by cabi.cu and pipeline.cu (not part of the C ABI).
+#pragma once
+
+#include "../../include/blt_cuda.h"
+#include "host_config.h"
+#include "kernels.cuh"
+
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace bltc {
+
+enum class Mode { Basic, Passthrough, BpePairs, BpeGeneral };
+
+int fail(int code, const std::string &msg);
+
+// Device scratch for one in-flight tokenization (look-back descriptors, multi-sweep ping-pong).
+struct Workspace {
+    void *d_scratch = nullptr;
+    size_t scratch_elems = 0;
+    bltk::SweepScratch scratch{};
+    uint8_t *d_work[2] = {nullptr, nullptr};  // general path: sweep ping-pong, 2*chunk bytes each
+    uint8_t *d_align = nullptr;               // general path: 16-byte aligned copy of a chunk
+    size_t work_chunk = 0;
+    uint64_t *h_ctrl = nullptr;               // pinned mirror of the scratch control block
+    int ensure_scratch(size_t n_elems);
+    int ensure_work(size_t chunk_bytes);
+    void release();
+};
+
+struct DeviceResult {
+    enum Kind { KNOWN, IN_SCRATCH } kind = KNOWN;  // IN_SCRATCH: length still in device memory
+    size_t len = 0;       // output bytes
+    uint32_t sweeps = 0;  // productive + verifying sweeps actually launched
+    int launches = 0;     // kernels enqueued
+};
+
+int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, size_t chunk, uint8_t *d_out,
+               size_t out_cap, uint64_t *d_chunk_ends, cudaStream_t stream, DeviceResult *res);
+int finish_result(Workspace &ws, cudaStream_t stream, DeviceResult *res);
+int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res);
+
+// One slot of the chunk pipeline: device in/out buffers plus the pinned words the kernel result is
+// copied into.  Pinned staging (h_in/h_out) is only allocated by the file-to-file pipeline.
+struct Slot {
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    uint8_t *h_in = nullptr, *h_out = nullptr;
+    uint64_t *h_ctrl = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
+    size_t in_len = 0;
+    DeviceResult res;
+};
+
+// The resources of one concurrent host call: three streams (H2D, compute, D2H) and S slots.
+struct Pipe {
+    int device = 0;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    std::vector<Slot> slots;
+    size_t cap = 0;        // input bytes per slot
+    bool pinned = false;   // slots own pinned staging
+    Workspace ws;
+    int ensure(size_t chunk_cap, size_t n_slots, bool want_pinned);
+    void release();
+};
+
+int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, int content_type, uint8_t *out,
+                  size_t out_cap, size_t *out_len);
+
+}  // namespace bltc
+
+struct blt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::mutex mu;
+    std::vector<std::unique_ptr<bltc::Pipe>> idle;  // pipes not currently lent to a call
+    std::unique_ptr<bltc::Pipe> acquire();
+    void give_back(std::unique_ptr<bltc::Pipe> p);
+};
+
+struct blt_strategy {
+    blt_ctx *ctx = nullptr;
+    bltc::Mode mode = bltc::Mode::Basic;
+    blth::MergeList rules;
+    uint16_t *d_table = nullptr;          // K2 byte-pair table
+    bltk::HashSlot *d_slots = nullptr;    // K3 hash table
+    uint32_t *d_can_left = nullptr, *d_can_right = nullptr;
+    uint32_t hash_mask = 0;
+    int variant = 0;                      // K2 tile configuration
+    std::mutex resident_mu;
+    bltc::Workspace resident;             // workspace of blt_process_resident
+    bltc::DeviceResult resident_result;
+    ~blt_strategy();
+};

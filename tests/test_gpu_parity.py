@@ -1,0 +1,396 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libblt_cuda.so), against the CPU
+oracle on the same inputs.  Bit-exact everywhere (byte / integer work, no tolerance).  Needs a B200:
+run with  python -m pytest tests -m gpu."""
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))
+DER = json.load(open(os.path.join(HERE, "golden", "derived_vectors.json")))
+BLT = os.path.join(ROOT, "blt_b200", "lib", "blt")
+MiB = 1 << 20
+
+
+def be(tokens):
+    return b"".join(int(t).to_bytes(2, "big") for t in tokens)
+
+
+def merges_dict(rows):
+    return {(a, b): v for a, b, v in rows}
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from blt_b200 import _native
+    return _native
+
+
+@pytest.fixture(scope="module")
+def ctx(nat):
+    c = nat.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+def resident(torch, strat, data: np.ndarray, chunk: int, want_ends: bool = True):
+    """blt_process_resident on torch-owned device memory; returns (output bytes, chunk_ends)."""
+    n = data.size
+    d_in = torch.from_numpy(np.ascontiguousarray(data)).cuda() if n else torch.empty(16, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(2 * n + 16, dtype=torch.uint8, device="cuda")
+    c = chunk if chunk else max(n, 1)
+    n_chunks = max(1, (n + c - 1) // c)
+    d_ends = torch.full((n_chunks,), -1, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    out_len = strat.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), 2 * n, d_ends.data_ptr() if want_ends else 0,
+                                     stream, sync=True)
+    return d_out[:out_len].cpu().numpy(), d_ends.cpu().numpy()
+
+
+# ---- reference-held golden vectors through the C ABI -------------------------------------------------
+
+@pytest.mark.parametrize("row", REF["bpe"], ids=lambda r: r["src"])
+def test_ref_bpe_vectors(ctx, row, tmp_path):
+    data = row["input"].encode()
+    if "merges_file" in row:
+        p = tmp_path / "merges.txt"
+        p.write_text(row["merges_file"])
+        s = ctx.bpe_from_file(str(p))
+    else:
+        s = ctx.bpe_from_pairs(merges_dict(row["merges"]))
+    assert s.process_chunk(data).tobytes() == be(row["tokens"])
+    assert s.tokenize_host(data, chunk_size=1 << 20).tobytes() == be(row["tokens"])
+
+
+@pytest.mark.parametrize("row", REF["basic"], ids=lambda r: r["src"])
+def test_ref_basic_vectors(ctx, row):
+    s = ctx.basic()
+    assert s.process_chunk(row["input"].encode()).tobytes() == bytes.fromhex(row["bytes_hex"])
+
+
+def test_ref_passthrough_and_content_type(ctx, nat):
+    for row in REF["passthrough"]:
+        assert ctx.passthrough().process_chunk(row["input"].encode()).tobytes() == bytes.fromhex(row["bytes_hex"])
+    row = REF["content_type"][0]
+    got = ctx.basic().tokenize_host(row["input"].encode(), 1 << 20, nat.CONTENT_TEXT)
+    assert got.tobytes() == bytes.fromhex(row["bytes_hex"])
+
+
+# ---- derived vectors: runs, overlaps, chains, cycles, chunk walls -------------------------------------
+
+@pytest.mark.parametrize("block", ["hand", "random"])
+def test_derived_vectors(ctx, torch_mod, block):
+    for row in DER[block]:
+        md = merges_dict(row["merges"])
+        data = np.frombuffer(bytes.fromhex(row["input_hex"]), dtype=np.uint8)
+        chunk = row["chunk"] or max(data.size, 1)
+        s = ctx.bpe_from_pairs(md)
+        assert s.tokenize_host(data, chunk_size=chunk).tobytes() == be(row["tokens"]), row
+        got, _ = resident(torch_mod, s, data, chunk)
+        assert got.tobytes() == be(row["tokens"]), row
+        s.close()
+
+
+# ---- random inputs vs the oracle, every tile configuration ---------------------------------------------
+
+def _random_case(rng, n, alphabet, density):
+    data = np.frombuffer(bytes(rng.choice(alphabet) for _ in range(n)), dtype=np.uint8) if n < 4096 else \
+        np.random.default_rng(rng.randrange(1 << 30)).choice(np.frombuffer(bytes(alphabet), dtype=np.uint8), size=n)
+    pairs = {}
+    for a in alphabet:
+        for b in alphabet:
+            if rng.random() < density:
+                pairs[(a, b)] = 256 + len(pairs)
+    return np.ascontiguousarray(data), pairs
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_random_vs_oracle_all_variants(nat, torch_mod, oracle, variant, monkeypatch):
+    monkeypatch.setenv("BLT_SWEEP_VARIANT", str(variant))
+    c = nat.Context(0)
+    rng = random.Random(1000 + variant)
+    sizes = [1, 2, 15, 16, 17, 255, 4095, 4096, 4097, 8191, 8193, 16384, 65537, 300001, 1 * MiB + 3, 5 * MiB + 11]
+    for n in sizes:
+        for density in (1.0, 0.85, 0.3):
+            alphabet = [97, 98, 99][: rng.choice([1, 2, 3])] if density == 1.0 else [97, 98, 99, 100, 32]
+            data, pairs = _random_case(rng, n, alphabet, density)
+            om = oracle.Merges(pairs)
+            s = c.bpe_from_pairs(pairs)
+            for chunk in (0, 4096, 65536, 100000, 1 * MiB):
+                if chunk > n and chunk != 0:
+                    continue
+                want = oracle.run_buffer("bpe", data, chunk or max(n, 1), 4, om)
+                got, ends = resident(torch_mod, s, data, chunk)
+                assert np.array_equal(got, want), (variant, n, density, chunk)
+                # chunk_ends is the inclusive prefix of per-chunk output lengths
+                cc = chunk or n
+                acc = 0
+                if (n + cc - 1) // cc > 64:
+                    assert int(ends[-1]) == want.size
+                    continue
+                for k in range((n + cc - 1) // cc):
+                    acc += len(oracle.process_chunk("bpe", data[k * cc:(k + 1) * cc], om))
+                    assert int(ends[k]) == acc, (variant, n, chunk, k)
+            got = s.tokenize_host(data, chunk_size=65536)
+            assert np.array_equal(got, oracle.run_buffer("bpe", data, 65536, 4, om))
+            s.close()
+    c.close()
+
+
+def test_long_runs_and_carry_chains(ctx, torch_mod, oracle):
+    """A whole chunk of one byte is a single run: parity must carry across threads, warps, tiles."""
+    pairs = {(97, 97): 256, (97, 98): 257, (98, 97): 258, (98, 98): 259}
+    om = oracle.Merges(pairs)
+    s = ctx.bpe_from_pairs(pairs)
+    n = 6 * MiB + 5
+    for head in (0, 1, 2, 3):
+        data = np.full(n, 97, dtype=np.uint8)
+        data[:head] = 99                      # shifts the run start, flipping every parity after it
+        data[3 * MiB + 77] = 99               # one break in the middle
+        for chunk in (0, 2 * MiB, 2 * MiB + 1, 1 * MiB + 4097):
+            got, _ = resident(torch_mod, s, data, chunk)
+            assert np.array_equal(got, oracle.run_buffer("bpe", data, chunk or n, 4, om)), (head, chunk)
+    ab = np.tile(np.frombuffer(b"ab", dtype=np.uint8), n // 2)
+    got, _ = resident(torch_mod, s, ab, 1 * MiB)
+    assert np.array_equal(got, oracle.run_buffer("bpe", ab, 1 * MiB, 4, om))
+
+
+def test_general_maps_multi_sweep(ctx, torch_mod, oracle):
+    """HashMap<(u16,u16),u16> beyond what merges.txt can express: chains, cycles, ids < 256."""
+    rng = random.Random(5)
+    cases = [
+        ({(97, 98): 256, (256, 99): 257, (257, 100): 258}, b"abcd" * 5000 + b"abc"),
+        ({(97, 97): 97}, b"a" * 100001),                               # cyclic, log2(n) sweeps
+        ({(97, 98): 99, (99, 98): 100}, b"abb" * 3333),                # chain through ids < 256
+        ({(120, 121): 90}, b"axyza" * 1000),
+        ({(97, 98): 256, (256, 256): 257, (257, 257): 258, (258, 258): 259}, b"ab" * 40000),
+    ]
+    for _ in range(6):
+        pool = [97, 98, 99, 256, 257, 258]
+        md = {(rng.choice(pool), rng.choice(pool)): rng.choice(pool + [300, 301]) for _ in range(8)}
+        if any(k[0] == v and k[1] == v for k, v in md.items()):
+            md = {k: v for k, v in md.items() if not (k[0] == v and k[1] == v)}
+        cases.append((md, bytes(rng.choice(b"abc") for _ in range(50000))))
+    for md, raw in cases:
+        data = np.frombuffer(raw, dtype=np.uint8)
+        om = oracle.Merges(md)
+        s = ctx.bpe_from_pairs(md)
+        want, sweeps = oracle.process_chunk("bpe", data, om, want_sweeps=True)
+        assert s.process_chunk(data).tobytes() == want, md
+        for chunk in (0, 4096, 10000, 10001):
+            got, ends = resident(torch_mod, s, data, chunk)
+            assert got.tobytes() == bytes(oracle.run_buffer("bpe", data, chunk or data.size, 2, om)), (md, chunk)
+            assert int(ends[(data.size + (chunk or data.size) - 1) // (chunk or data.size) - 1]) == got.size
+        s.close()
+
+
+def test_basic_random_and_ragged(ctx, torch_mod, oracle):
+    from blt_b200 import synth
+    s = ctx.basic()
+    for n in (0, 1, 15, 16, 17, 4097, 1 * MiB + 7, 32 * MiB + 5):
+        data = synth.random_bytes(n, 77 + n)
+        want = oracle.run_buffer("basic", data, 1 << 22, 4)
+        if n:
+            got, ends = resident(torch_mod, s, data, 1 << 22)
+            assert np.array_equal(got, want)
+            assert int(ends[-1]) == 2 * n
+        assert np.array_equal(s.tokenize_host(data, chunk_size=1 << 22), want)
+        assert np.array_equal(s.process_chunk(data), np.frombuffer(oracle.process_chunk("basic", data), dtype=np.uint8))
+
+
+def test_empty_and_capacity_errors(ctx, nat, torch_mod):
+    s = ctx.bpe_from_pairs({(97, 98): 256})
+    assert s.process_chunk(b"").size == 0                      # tokenizer.rs:57-59
+    assert s.tokenize_host(b"", chunk_size=1024).size == 0     # pipeline.rs:103-105
+    assert ctx.basic().tokenize_host(b"", 1024, nat.CONTENT_BIN).tobytes() == b"\xff\x03"
+    small = np.empty(10, dtype=np.uint8)
+    with pytest.raises(nat.BltError) as ei:
+        s.process_chunk(b"x" * 1000, out=small)
+    assert ei.value.code == nat.ERR_CAPACITY
+    with pytest.raises(nat.BltError) as ei:                    # misaligned device pointer
+        d = torch_mod.zeros(64, dtype=torch_mod.uint8, device="cuda")
+        s.process_resident(d.data_ptr() + 1, 16, 0, d.data_ptr(), 32)
+    assert ei.value.code == nat.ERR_INVALID_INPUT
+
+
+def test_concurrent_process_chunk_on_one_strategy(ctx, oracle):
+    """TokenizationStrategy is Send + Sync: up to num_threads calls at once (pipeline.rs:86-97)."""
+    import threading
+    from blt_b200 import synth
+    data = synth.text(8 * MiB, 99)
+    l, r = synth.merges_from_sample(data, 500)
+    pairs = {(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))}
+    s = ctx.bpe_from_pairs(pairs)
+    om = oracle.Merges(pairs)
+    want = [np.frombuffer(oracle.process_chunk("bpe", data[k * MiB:(k + 1) * MiB], om), dtype=np.uint8) for k in range(8)]
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                if not np.array_equal(s.process_chunk(data[k * MiB:(k + 1) * MiB]), want[k]):
+                    errs.append(k)
+        except Exception as e:  # pragma: no cover
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+
+
+# ---- the five BASELINE.json configs ----------------------------------------------------------------------
+
+def _check_chunks(torch, oracle, om, data, d_out_np, ends, chunk, which, mode="bpe"):
+    for k in which:
+        lo = 0 if k == 0 else int(ends[k - 1])
+        want = np.frombuffer(oracle.process_chunk(mode, data[k * chunk:(k + 1) * chunk], om), dtype=np.uint8)
+        assert np.array_equal(d_out_np[lo:int(ends[k])], want), k
+
+
+def test_config1_basic_100mib(ctx, torch_mod, oracle):
+    from blt_b200 import synth
+    n = 100 * MiB
+    data = synth.random_bytes(n, synth.SEED_CONFIG[1])
+    got, ends = resident(torch_mod, ctx.basic(), data, 16 * MiB)
+    assert got.size == 209715200
+    assert np.array_equal(got, oracle.run_buffer("basic", data, 16 * MiB, 8))
+
+
+def test_config2_bpe256_100mib(ctx, torch_mod, oracle, tmp_path):
+    from blt_b200 import synth
+    n = 100 * MiB
+    data = synth.text(n, synth.SEED_CONFIG[2])
+    l, r = synth.merges_from_sample(data, 256)
+    synth.write_merges_file(str(tmp_path / "m.txt"), l, r)
+    s = ctx.bpe_from_file(str(tmp_path / "m.txt"))
+    om = oracle.Merges.from_file(str(tmp_path / "m.txt"))
+    want = oracle.run_buffer("bpe", data, 16 * MiB, os.cpu_count() or 4, om)
+    got, ends = resident(torch_mod, s, data, 16 * MiB)
+    assert np.array_equal(got, want)
+    assert np.array_equal(s.tokenize_host(data, chunk_size=16 * MiB), want)
+
+
+@pytest.mark.parametrize("cfg", [3, 4])
+def test_config3_and_4_one_gib(ctx, torch_mod, oracle, tmp_path, cfg):
+    """1 GiB device-resident.  Checked against the oracle chunk by chunk on a sample of chunks (the
+    oracle needs ~10 s per GiB per 64 cores) and through size-independent properties on the whole."""
+    from blt_b200 import synth
+    torch = torch_mod
+    n, chunk = 1 << 30, 16 * MiB
+    if cfg == 3:
+        data = synth.text(n, synth.SEED_CONFIG[3])
+        l, r = synth.merges_from_sample(data, 32768)
+        synth.write_merges_file(str(tmp_path / "m.txt"), l, r)
+        s = ctx.bpe_from_file(str(tmp_path / "m.txt"))
+        om = oracle.Merges.from_file(str(tmp_path / "m.txt"))
+        assert s.num_merges == 32768 and max(om.to_dict().values()) == 33023
+    else:
+        data = synth.adversarial(n, synth.SEED_CONFIG[4])
+        pairs = {p: 256 + i for i, p in enumerate(synth.adversarial_pairs())}
+        s = ctx.bpe_from_pairs(pairs)
+        om = oracle.Merges(pairs)
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    d_ends = torch.zeros(n // chunk, dtype=torch.int64, device="cuda")
+    out_len = s.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), 2 * n, d_ends.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+    ends = d_ends.cpu().numpy()
+    out = d_out[:out_len].cpu().numpy()
+    assert int(ends[-1]) == out_len and np.all(np.diff(ends) > 0)
+    _check_chunks(torch, oracle, om, data, out, ends, chunk, [0, 1, 17, 31, 32, 63])
+    # property: every chunk's tokens decode back to exactly that chunk's bytes
+    first_of = np.arange(65536, dtype=np.int64)
+    second_of = np.zeros(65536, dtype=np.int64)
+    for (a, b), v in om.to_dict().items():
+        first_of[v], second_of[v] = a, b
+    for k in (5, 40):
+        lo = 0 if k == 0 else int(ends[k - 1])
+        toks = out[lo:int(ends[k])].view(">u2").astype(np.int64)
+        merged = toks >= 256
+        width = 1 + merged.astype(np.int64)
+        assert int(width.sum()) == chunk                          # each merge removes exactly one symbol
+        pos = np.cumsum(width) - width
+        rec = np.zeros(chunk, dtype=np.uint8)
+        rec[pos] = first_of[toks]
+        rec[pos[merged] + 1] = second_of[toks[merged]]
+        assert np.array_equal(rec, data[k * chunk:(k + 1) * chunk]), k
+    # property: idempotence of the launch (same input, same table -> same bytes)
+    d_out2 = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    out_len2 = s.process_resident(d_in.data_ptr(), n, chunk, d_out2.data_ptr(), 2 * n, 0, torch.cuda.current_stream().cuda_stream)
+    assert out_len2 == out_len and torch.equal(d_out2[:out_len2], d_out[:out_len])
+    if cfg == 4:   # chain maps through the pair API on a 64 MiB slice
+        sl = data[: 64 * MiB]
+        md = {(97, 98): 99, (99, 98): 100, (97, 97): 256, (256, 256): 257, (100, 100): 97}
+        sg = ctx.bpe_from_pairs(md)
+        got, _ = resident(torch, sg, sl, chunk)
+        assert np.array_equal(got, oracle.run_buffer("bpe", sl, chunk, os.cpu_count() or 4, oracle.Merges(md)))
+
+
+# ---- file to file: CLI and Python binding -------------------------------------------------------------------
+
+def test_cli_file_to_file_and_stdin(oracle, tmp_path):
+    from blt_b200 import synth
+    data = synth.text(5 * MiB + 321, 4242)
+    (tmp_path / "in.bin").write_bytes(data.tobytes())
+    l, r = synth.merges_from_sample(data, 300)
+    synth.write_merges_file(str(tmp_path / "m.txt"), l, r)
+    om = oracle.Merges.from_file(str(tmp_path / "m.txt"))
+    # tests/cli.rs:46-80 (file -> file, basic), with default chunking
+    assert subprocess.run([BLT, "--input", str(tmp_path / "in.bin"), "--output", str(tmp_path / "o1.bin")]).returncode == 0
+    assert (tmp_path / "o1.bin").read_bytes() == bytes(oracle.run_buffer("basic", data, 16 * MiB, 4))
+    # BPE, explicit chunk size (clamped up to 256 KiB, chunking.rs:29), content-type prefix
+    for cs, eff in (("1KB", 256 * 1024), ("1MB", MiB), ("300000", 300000)):
+        assert subprocess.run([BLT, "-i", str(tmp_path / "in.bin"), "-o", str(tmp_path / "o2.bin"), "--merges",
+                               str(tmp_path / "m.txt"), "--chunksize", cs, "--type", "text", "--threads", "2"]).returncode == 0
+        assert (tmp_path / "o2.bin").read_bytes() == bytes(oracle.run_buffer("bpe", data, eff, 4, om, 0xFF01)), cs
+    # stdin -> stdout rows of tests/cli.rs
+    r = subprocess.run([BLT], input=b"hello world", capture_output=True)
+    assert r.returncode == 0 and r.stdout == bytes(oracle.run_buffer("basic", b"hello world", 1 << 20, 1))
+    r = subprocess.run([BLT, "--type", "text"], input=b"test", capture_output=True)
+    assert r.stdout == b"\xff\x01\x00t\x00e\x00s\x00t"
+    (tmp_path / "ab.txt").write_text("97 98\n")
+    r = subprocess.run([BLT, "--merges", str(tmp_path / "ab.txt")], input=b"ab c ab", capture_output=True)
+    assert r.stdout == be([256, 32, 99, 32, 256])
+    r = subprocess.run([BLT, "--chunksize", "1KB"], input=b"some data", capture_output=True)
+    assert r.stdout == bytes(oracle.run_buffer("basic", b"some data", 1 << 20, 1))
+    # empty file -> empty output
+    (tmp_path / "empty").write_bytes(b"")
+    assert subprocess.run([BLT, "-i", str(tmp_path / "empty"), "-o", str(tmp_path / "o3.bin"), "--merges", str(tmp_path / "m.txt")]).returncode == 0
+    assert (tmp_path / "o3.bin").read_bytes() == b""
+
+
+def test_python_bytetokenizer(oracle, tmp_path):
+    """The value-free smoke tests of blt_python/tests/test_tokenizer.py, with the values pinned."""
+    import blt_b200
+    (tmp_path / "in.bin").write_bytes(b"hello world")
+    blt_b200.ByteTokenizer().tokenize_file(str(tmp_path / "in.bin"), str(tmp_path / "out.bin"))
+    assert (tmp_path / "out.bin").read_bytes() == bytes(oracle.run_buffer("basic", b"hello world", 1 << 20, 1))
+    (tmp_path / "in.bin").write_bytes(b"ab")
+    blt_b200.ByteTokenizer(merges={(97, 98): 256}).tokenize_file(str(tmp_path / "in.bin"), str(tmp_path / "out.bin"))
+    assert (tmp_path / "out.bin").read_bytes() == b"\x01\x00"
+    (tmp_path / "in.bin").write_bytes(b"")
+    blt_b200.ByteTokenizer().tokenize_file(str(tmp_path / "in.bin"), str(tmp_path / "out.bin"))
+    assert (tmp_path / "out.bin").read_bytes() == b""
+    big = b"x" * (100 * 1024)
+    (tmp_path / "in.bin").write_bytes(big)
+    t = blt_b200.ByteTokenizer(threads=2, chunk_size="1MB", memory_cap=50, content_type="Bin")
+    t.tokenize_file(str(tmp_path / "in.bin"), str(tmp_path / "out.bin"))
+    assert (tmp_path / "out.bin").read_bytes() == b"\xff\x03" + bytes(oracle.run_buffer("basic", big, 1 << 20, 1))
+    with pytest.raises(FileNotFoundError):
+        blt_b200.ByteTokenizer().tokenize_file(str(tmp_path / "nope"), str(tmp_path / "out.bin"))

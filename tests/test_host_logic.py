@@ -1,0 +1,199 @@
+"""CPU-only checks of the product's host side (libblt_cuda.so without a device): the C ABI exports
+every symbol the header declares, the merges loader / size grammar / chunk sizing / thread count
+reproduce the reference's golden vectors, the Python surface mirrors blt_python's, and every compute
+entry point fails loudly without a CUDA device (no CPU fallback)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+import blt_b200
+from blt_b200 import _native as nat
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))
+BLT = os.path.join(ROOT, "blt_b200", "lib", "blt")
+
+
+def has_gpu() -> bool:
+    try:
+        return nat.device_count() > 0
+    except nat.BltError:
+        return False
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "blt_cuda.h")).read()
+    declared = set(re.findall(r"BLT_API\s+[\w\s\*]+?\b(blt_\w+)\s*\(", hdr))
+    assert len(declared) >= 20, declared
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", nat.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (blt_\w+)", out))
+    assert declared <= exported
+    assert exported - declared == set(), "exported but undeclared: %s" % (exported - declared)
+
+
+def test_version_matches_reference_package_version():
+    assert blt_b200.version() == "0.2.2" == blt_b200.__version__ == nat.version()
+
+
+@pytest.mark.parametrize("row", REF["merges_files"], ids=lambda r: r["src"])
+def test_product_loader_golden(row, tmp_path):
+    p = tmp_path / "m.txt"
+    p.write_text(row["text"])
+    want = {(a, b): v for a, b, v in row["map"]}
+    assert nat.load_bpe_merges(str(p)) == want
+    assert blt_b200.load_bpe_merges(str(p)) == want
+
+
+@pytest.mark.parametrize("row", REF["merges_file_errors"], ids=lambda r: r["src"])
+def test_product_loader_errors(row, tmp_path):
+    kinds = {"InvalidData": nat.ERR_INVALID_DATA, "NotFound": nat.ERR_NOT_FOUND}
+    p = tmp_path / "m.txt"
+    if not row.get("missing_file"):
+        p.write_text(row["text"])
+    with pytest.raises(nat.BltError) as ei:
+        nat.load_bpe_merges(str(p))
+    assert ei.value.code == kinds[row["kind"]]
+    if "contains" in row:
+        assert row["contains"] in ei.value.message
+    # Python surface: IOError for a missing file (blt_python/tests/test_tokenizer.py:229-232)
+    with pytest.raises((IOError, ValueError)):
+        blt_b200.load_bpe_merges(str(p))
+
+
+def test_product_loader_matches_oracle_on_corner_cases(oracle, tmp_path):
+    cases = [b"97 98", b"97 98\r\n99 100\r\n", b"  97\t 98  \n", b"+97 098\n", b"\n\n#x\n0 0\n255 255\n",
+             b" # not a comment\n", b"   \n", b"97 98 # c\n", b"-1 5\n", b"5 300\n", b"5 +\n", b"1.0 2\n",
+             b"97 98\n\xff\xfe\n", b"1 2\n1 2\n1 2\n", b"97\xc2\xa098\n", b"97 98\r", b"#\n", b"256 1\n", b"1 2 3\n",
+             b"9999999999999999999999 1\n", b"12a 1\n", b"1 \xe2\x80\x8398\n"]
+    for i, raw in enumerate(cases):
+        p = tmp_path / f"c{i}.txt"
+        p.write_bytes(raw)
+        try:
+            want = ("ok", oracle.Merges.from_file(str(p)).to_dict())
+        except oracle.OracleError as e:
+            want = ("err", e.kind, e.message)
+        try:
+            got = ("ok", nat.load_bpe_merges(str(p)))
+        except nat.BltError as e:
+            got = ("err", e.code, e.message)
+        assert got == want, raw
+    lines = "".join(f"{i % 256} {(i // 256) % 256}\n" for i in range(65280))
+    (tmp_path / "big.txt").write_text(lines)
+    assert max(nat.load_bpe_merges(str(tmp_path / "big.txt")).values()) == 65535
+    (tmp_path / "big.txt").write_text(lines + "1 1\n")
+    with pytest.raises(nat.BltError):
+        nat.load_bpe_merges(str(tmp_path / "big.txt"))
+
+
+def test_chunk_size_grammar_and_clamps(oracle):
+    for s, v in REF["chunk_size_parse"]["valid"]:
+        assert nat.parse_chunk_size(s) == v
+    for s in REF["chunk_size_parse"]["invalid"] + ["+", "1 KB", "99999999999999999999", "18014398509481984KB"]:
+        with pytest.raises(nat.BltError) as ei:
+            nat.parse_chunk_size(s)
+        assert ei.value.code == nat.ERR_INVALID_INPUT
+        with pytest.raises(oracle.OracleError):
+            oracle.parse_chunk_size(s)
+    for s in ["+5KB", "007", "0", "16mb", "\t3Mb\n", "1kB "]:
+        assert nat.parse_chunk_size(s) == oracle.parse_chunk_size(s)
+    for cli, want in REF["chunk_size_clamp"]["cases"]:
+        assert nat.effective_chunk_size(cli, 4, 80, 64 << 30) == want
+    for ram in [1 << 28, 1 << 30, 8 << 30, 64 << 30, 2 << 40]:
+        for threads in [1, 4, 128, 1000]:
+            for cap in [0, 1, 50, 80, 100]:
+                assert nat.effective_chunk_size(None, threads, cap, ram) == oracle.effective_chunk_size(None, threads, cap, ram)
+    assert (1 << 20) <= nat.effective_chunk_size(None, 4, 80, 0) <= (16 << 20)   # probes this host
+
+
+def test_thread_count_and_content_type_tokens():
+    for v, want in REF["thread_count"]["cases"]:
+        assert nat.determine_thread_count(v) == want
+    assert nat.determine_thread_count(None) == len(os.sched_getaffinity(0))
+    t = REF["content_type_tokens"]
+    assert [nat.content_type_token(i) for i in range(4)] == [t["text"], t["audio"], t["bin"], t["video"]]
+    assert nat.content_type_token(-1) == 0
+
+
+def test_shard_chunks_is_floor_k_g_over_k():
+    for n_chunks in [1, 2, 7, 64, 65, 512, 513]:
+        for g in [1, 2, 3, 4, 8]:
+            b = nat.shard_chunks(n_chunks, g)
+            assert b[0] == 0 and b[-1] == n_chunks and all(x <= y for x, y in zip(b, b[1:]))
+            for k in range(n_chunks):
+                owner = (k * g) // n_chunks
+                assert b[owner] <= k < b[owner + 1]
+
+
+# ---- Python surface, mirroring blt_python/tests/test_tokenizer.py (the rows that need no device) ----
+
+def test_python_surface_shape():
+    for name in ["ByteTokenizer", "load_bpe_merges", "version", "__version__"]:
+        assert hasattr(blt_b200, name)
+    t = blt_b200.ByteTokenizer()
+    assert "ByteTokenizer" in str(t)
+    assert repr(t) == "ByteTokenizer(merges=0, content_type=None, threads=None, chunk_size=None, memory_cap=None)"
+    assert "merges=2" in str(blt_b200.ByteTokenizer(merges={(97, 98): 256, (99, 100): 257}))
+    assert 'content_type=Some("Text")' in str(blt_b200.ByteTokenizer(content_type="Text"))
+    assert 'content_type=Some("Bin")' in str(blt_b200.ByteTokenizer(content_type="Bin"))
+    assert repr(blt_b200.ByteTokenizer(threads=2, chunk_size="1MB", memory_cap=50)).endswith(
+        'threads=Some(2), chunk_size=Some("1MB"), memory_cap=Some(50))')
+    with pytest.raises(ValueError):
+        blt_b200.ByteTokenizer(content_type="Invalid")
+    with pytest.raises(ValueError):
+        blt_b200.ByteTokenizer(memory_cap=150)
+    with pytest.raises(IOError):
+        blt_b200.load_bpe_merges("non_existent_file.txt")
+
+
+# ---- no CPU fallback --------------------------------------------------------------------------------
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a CUDA device")
+def test_compute_fails_loudly_without_a_device(tmp_path):
+    with pytest.raises(nat.BltError) as ei:
+        nat.Context(0)
+    assert ei.value.code == nat.ERR_NO_DEVICE
+    (tmp_path / "in.bin").write_bytes(b"hello world")
+    with pytest.raises(RuntimeError):
+        blt_b200.ByteTokenizer().tokenize_file(str(tmp_path / "in.bin"), str(tmp_path / "out.bin"))
+    r = subprocess.run([BLT, "-i", str(tmp_path / "in.bin"), "-o", str(tmp_path / "o2.bin")], capture_output=True)
+    assert r.returncode == 1 and b"Error running tokenizer" in r.stderr
+
+
+# ---- CLI surface that needs no device (src/main.rs:8-106) ---------------------------------------------
+
+def test_cli_flags_and_exit_codes(tmp_path):
+    r = subprocess.run([BLT, "--version"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "blt 0.2.2"
+    r = subprocess.run([BLT, "--help"], capture_output=True, text=True)
+    for flag in ["-i, --input", "-o, --output", "--merges", "--passthrough", "--type", "--threads", "--memcap",
+                 "--chunksize", "-h, --help", "-V, --version"]:
+        assert flag in r.stdout
+    # passthrough is a copy: tests/cli.rs:196-214 (stdin -> stdout), and file -> file
+    r = subprocess.run([BLT, "--passthrough"], input=b"passthrough test", capture_output=True)
+    assert r.returncode == 0 and r.stdout == b"passthrough test"
+    r = subprocess.run([BLT, "--passthrough", "--type", "video"], input=b"x", capture_output=True)
+    assert r.stdout == b"\xff\x04x"
+    (tmp_path / "in.bin").write_bytes(b"abc" * 1000)
+    r = subprocess.run([BLT, "--passthrough", "-i", str(tmp_path / "in.bin"), "-o", str(tmp_path / "out.bin")])
+    assert r.returncode == 0 and (tmp_path / "out.bin").read_bytes() == b"abc" * 1000
+    # clap usage errors -> exit 2
+    for bad in [["--type", "TEXT"], ["--threads", "x"], ["--memcap", "256"], ["--bogus"], ["--merges"], ["-m", "x"]]:
+        assert subprocess.run([BLT] + bad, capture_output=True, input=b"").returncode == 2, bad
+    # CoreConfig::new_from_cli errors -> `Error: ...`, exit 1, before any IO happens
+    out = tmp_path / "never.bin"
+    r = subprocess.run([BLT, "--chunksize", "1gb", "-o", str(out)], capture_output=True, input=b"x")
+    assert r.returncode == 1 and b"InvalidInput" in r.stderr and not out.exists()
+    (tmp_path / "bad.txt").write_text("97 abc\n")
+    r = subprocess.run([BLT, "--merges", str(tmp_path / "bad.txt"), "-o", str(out)], capture_output=True, input=b"x")
+    assert r.returncode == 1 and b"Failed to load BPE merges: Failed to parse second byte value" in r.stderr
+    assert not out.exists()
+    r = subprocess.run([BLT, "--passthrough", "-i", str(tmp_path / "missing")], capture_output=True)
+    assert r.returncode == 1 and b"Error running tokenizer" in r.stderr

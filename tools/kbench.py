@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmark: device-resident timings (CUDA events) of K1 (widen) and of every K2 tile
+configuration on the BASELINE.json workloads.  Prints one JSON line per measurement.
+    python tools/kbench.py [--bytes N] [--iters K] [--variants 0,1,2] [--configs 1,2,3,4]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from blt_b200 import _native as nat, synth  # noqa: E402
+
+VARIANT_NAMES = ["g256r2", "g512r1", "g512r2", "g1024r1", "g256r1", "g128r2"]
+
+
+def time_resident(strat, d_in, n, chunk, d_out, iters):
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        strat.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), d_out.numel(), 0, stream, sync=False)
+    out_len, _ = strat.resident_result(stream)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        a.record()
+        strat.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), d_out.numel(), 0, stream, sync=False)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    return out_len, ms[len(ms) // 2], ms[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bytes", type=int, default=1 << 30)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--variants", default="0,1,2,3,4,5")
+    ap.add_argument("--configs", default="1,2,3,4")
+    args = ap.parse_args()
+    n, chunk = args.bytes, 16 << 20
+    peak = 6555.5
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p))["hbm_gbs"])
+    torch.cuda.set_device(0)
+    d_out = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    for cfg in [int(c) for c in args.configs.split(",")]:
+        if cfg == 1:
+            data = synth.random_bytes(n, synth.SEED_CONFIG[1])
+        elif cfg == 4:
+            data = synth.adversarial(n, synth.SEED_CONFIG[4])
+        else:
+            data = synth.text(n, synth.SEED_CONFIG[cfg])
+        d_in = torch.from_numpy(data).cuda()
+        variants = [None] if cfg == 1 else [int(v) for v in args.variants.split(",")]
+        for v in variants:
+            if v is not None:
+                os.environ["BLT_SWEEP_VARIANT"] = str(v)
+            ctx = nat.Context(0)
+            if cfg == 1:
+                strat, name = ctx.basic(), "widen"
+            elif cfg == 4:
+                strat = ctx.bpe_from_pairs({p_: 256 + i for i, p_ in enumerate(synth.adversarial_pairs())})
+                name = VARIANT_NAMES[v]
+            else:
+                l, r = synth.merges_from_sample(data, 256 if cfg == 2 else 32768)
+                strat = ctx.bpe_from_pairs({(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))})
+                name = VARIANT_NAMES[v]
+            out_len, med, best = time_resident(strat, d_in, n, chunk, d_out, args.iters)
+            alg = n + out_len
+            print(json.dumps({"config": cfg, "kernel": name, "n": n, "out_bytes": out_len, "ratio_tokens_per_byte": round(out_len / 2 / n, 4),
+                              "ms_median": round(med, 4), "ms_best": round(best, 4), "input_GBps": round(n / med / 1e6, 1),
+                              "algorithmic_GBps": round(alg / med / 1e6, 1), "frac_of_measured_hbm": round(alg / med / 1e6 / peak, 4)}),
+                  flush=True)
+            strat.close()
+            ctx.close()
+        del d_in
+
+
+if __name__ == "__main__":
+    main()
