@@ -247,6 +247,13 @@ blt_strategy::~blt_strategy() {
 
 using namespace bltc;
 
+#ifdef BLT_TRACE
+namespace bltk { cudaError_t debug_set_trace(unsigned long long *d_buf, unsigned int iters); }
+extern "C" __attribute__((visibility("default"))) int blt_debug_set_trace(void *d_buf, unsigned int iters) {
+    return bltk::debug_set_trace(static_cast<unsigned long long *>(d_buf), iters) == cudaSuccess ? 0 : -5;
+}
+#endif
+
 extern "C" {
 
 const char *blt_version(void) { return BLT_VERSION_STRING; }

@@ -22,7 +22,7 @@ __host__ __device__ inline uint32_t pair_table_index(uint32_t b0, uint32_t b1) {
     // Bank (= bits 1..5 of the u16 index) mixes both bytes so lanes holding the same frequent
     // first byte with different second bytes do not collide.
     const uint32_t x = b0 | (b1 << 8);
-    return x ^ ((x >> 7) & 0x3Eu);
+    return x ^ (x >> 7);  // xorshift: a bijection on 16 bits
 }
 
 // General map for K3: open addressing, linear probing, 8-byte slots.
@@ -44,12 +44,14 @@ struct HashTableView {
 
 // Per-launch scratch in device memory (zeroed by the launcher before every sweep).
 struct SweepScratch {
-    void *ctrl;              // start of the region: 64-byte control block, then the descriptors
-    uint64_t *total_tokens;  // ctrl+0 : number of tokens written by the sweep
-    uint32_t *tile_counter;  // ctrl+8 : dynamic tile id dispenser
-    uint32_t *merged_any;    // ctrl+12: set to 1 if any pair merged in this sweep
-    uint32_t *overflow;      // ctrl+16: set to 1 if the output capacity was exceeded
-    uint64_t *tile_status;   // ctrl+64: one word per tile (look-back descriptors)
+    void *ctrl;              // start of the region: 512-byte control block, then the descriptors
+    uint64_t *total_tokens;  // ctrl+0  : number of tokens written by the sweep
+    uint32_t *merged_any;    // ctrl+12 : set to 1 if any pair merged in this sweep
+    uint32_t *overflow;      // ctrl+16 : set to 1 if the output capacity was exceeded
+    uint32_t *tile_counter;  // ctrl+128: dynamic tile id dispenser (own 128-byte line)
+    uint32_t *phase_hint;    // ctrl+256: (unused since tiles are assigned statically)
+    uint32_t *dense_abort;   // ctrl+384: set by the dense kernel when its speculation fails (own line)
+    uint64_t *tile_status;   // ctrl+512: one word per tile (look-back descriptors)
     size_t bytes;            // size of the whole region
     size_t max_tiles;
 };
@@ -68,6 +70,7 @@ struct SweepArgs {
     size_t out_base_tokens;  // the first token of this sweep lands at out[out_base_tokens]
     uint64_t *chunk_ends;    // optional device array: inclusive prefix of OUTPUT BYTES per chunk
     size_t chunk_ends_base;  // bytes added to every chunk_ends entry (output before this launch)
+    const uint32_t *dense_flag;  // non-null: a dense pass ran first; *dense_flag == 0 means it succeeded
     SweepScratch scratch;
 };
 

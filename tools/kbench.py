@@ -15,7 +15,7 @@ import torch  # noqa: E402
 
 from blt_b200 import _native as nat, synth  # noqa: E402
 
-VARIANT_NAMES = ["g256r2", "g512r1", "g512r2", "g1024r1", "g256r1", "g128r2"]
+VARIANT_NAMES = ["g1024r2", "g1024r1", "g512r2", "g256r2", "g512r1", "g256r1"]
 
 
 def time_resident(strat, d_in, n, chunk, d_out, iters):
