@@ -496,26 +496,33 @@ dense_pairs_kernel(const unsigned char *__restrict__ in, unsigned long long n, u
     const unsigned long long n_segs = n / 16;
     const unsigned long long stride = (unsigned long long)gridDim.x * kCtaThreads;
     unsigned long long seg = (unsigned long long)blockIdx.x * kCtaThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     bool bad = false;
-    // two independent 16-byte loads in flight per thread
-    for (; seg + stride < n_segs; seg += 2 * stride) {
-        const uint4 w0 = ldg_stream_v4(in + seg * 16);
-        const uint4 w1 = ldg_stream_v4(in + (seg + stride) * 16);
-        const uint32_t ab = *reinterpret_cast<volatile uint32_t *>(abort_flag);
-        uint32_t v0[4], v1[4];
-        fe.lookup_vals(w0, 0u, 0u, v0);
-        fe.lookup_vals(w1, 0u, 0u, v1);
-        bad = bad || !PairsFE::all_present(v0) || !PairsFE::all_present(v1);
-        stg_stream_v4(out + seg * 8, make_uint4(v0[0], v0[1], v0[2], v0[3]));
-        stg_stream_v4(out + (seg + stride) * 8, make_uint4(v1[0], v1[1], v1[2], v1[3]));
-        if (ab | uint32_t(__any_sync(FULL, bad))) break;  // somebody (maybe this warp) gave up: stop streaming
+    uint32_t ab = 0;  // the abort word as it was one trip ago: never waited for inside a trip
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    for (; seg + (U - 1) * stride < n_segs; seg += U * stride) {
+        uint4 w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) w[u] = ldg_stream_v4(in + (seg + u * stride) * 16);
+        const uint32_t ab_now = ab;
+        if (lane == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(abort_flag) : "memory");
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t v[4];
+            fe.lookup_vals(w[u], 0u, 0u, v);
+            bad = bad || !PairsFE::all_present(v);
+            stg_stream_v4(out + (seg + u * stride) * 8, make_uint4(v[0], v[1], v[2], v[3]));
+        }
+        if (__any_sync(FULL, bad || ab_now != 0)) break;  // this warp or somebody else gave up: stop streaming
     }
-    if (!bad && seg < n_segs && seg + stride >= n_segs) {
-        const uint4 w0 = ldg_stream_v4(in + seg * 16);
-        uint32_t v0[4];
-        fe.lookup_vals(w0, 0u, 0u, v0);
-        bad = !PairsFE::all_present(v0);
-        stg_stream_v4(out + seg * 8, make_uint4(v0[0], v0[1], v0[2], v0[3]));
+    if (!__any_sync(FULL, bad || ab != 0)) {
+        for (; seg < n_segs; seg += stride) {
+            const uint4 w0 = ldg_stream_v4(in + seg * 16);
+            uint32_t v[4];
+            fe.lookup_vals(w0, 0u, 0u, v);
+            bad = bad || !PairsFE::all_present(v);
+            stg_stream_v4(out + seg * 8, make_uint4(v[0], v[1], v[2], v[3]));
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the last n % 16 elements
         unsigned long long i = n_segs * 16;
