@@ -147,6 +147,35 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def pcie_probe(torch, h_in, h_out, d_in, d_out, n):
+    """Pinned cudaMemcpyAsync ceilings on this box: H2D alone, D2H alone, both directions at once
+    (what the e2e pipeline is bounded by: it moves n bytes in and the output back, concurrently)."""
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d, d2h):
+        best = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s1.wait_stream(torch.cuda.current_stream())
+            s2.wait_stream(torch.cuda.current_stream())
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out[:n].copy_(d_out[:n], non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s1)
+            torch.cuda.current_stream().wait_stream(s2)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return round(n / best / 1e6, 2)
+
+    return {"h2d": run(True, False), "d2h": run(False, True), "both_directions_each": run(True, True)}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -261,7 +290,8 @@ def run_ours(args):
         if not args.no_check:
             if not torch.equal(h_out[:got], d_out[:out_bytes].cpu()):
                 raise SystemExit("PARITY FAILURE: e2e output differs from the device-resident output")
-        e2e = {"value": round(world * n * e_steps / (e_ms * 1e-3) / 1e9, 3), "unit": "GB/s",
+        pcie = pcie_probe(torch, h_in, h_out, d_in, d_out, n) if rank == 0 else None
+        e2e = {"value": round(world * n * e_steps / (e_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "pcie_probe_GBps": pcie,
                "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(out_bytes), "steps": e_steps,
                "ms_per_step": round(e_ms / e_steps, 3)}
 

@@ -198,40 +198,52 @@ __device__ __noinline__ bool decoupled_lookback(const uint64_t *status, long lon
 #define DBG_DONE() do { } while (0)
 #endif
     // ---------------- fast fold ----------------
+    // Row-major polling: row i, lane l reads tile j - (32*i + l), so every row is one coalesced 256-byte
+    // request (entry 0 = nearest predecessor).
     {
         uint64_t sum = 0;
         long long j = tile - 1;
-        bool alive = true;
-        while (alive) {
+        for (;;) {
             uint64_t st[LW];
-            int lp = LW, lz = LW;  // nearest PREFIX / nearest not-ready entry among this lane's LW
+            uint32_t pmask[LW], zmask[LW];
 #pragma unroll
-            for (int i = LW - 1; i >= 0; --i) {
-                const long long idx = j - (long long)(lane * LW + i);  // i = 0 is the nearest
+            for (int i = 0; i < LW; ++i) {
+                const long long idx = j - (long long)(i * 32 + lane);
                 st[i] = (idx >= 0) ? ld_relaxed_u64(status + idx) : ST_PREFIX;  // virtual tile -1
-                const uint32_t state = uint32_t(st[i] >> 62);
-                if (state == 2) lp = i;
-                if (state == 0) lz = i;
             }
-            const uint32_t pm = __ballot_sync(FULL, lp < LW);
-            const int p_lane = pm ? (__ffs(pm) - 1) : 32;
-            const int p_sub = pm ? __shfl_sync(FULL, lp, p_lane & 31) : LW;
-            const bool bad = (lane < p_lane && lz < LW) || (lane == p_lane && lz < p_sub);
+            int ip = LW;          // row of the nearest PREFIX
+            uint32_t below = FULL;  // lanes of that row that are nearer than the PREFIX
+            bool ready = true;
+#pragma unroll
+            for (int i = 0; i < LW; ++i) {
+                const uint32_t state = uint32_t(st[i] >> 62);
+                pmask[i] = __ballot_sync(FULL, state == 2);
+                zmask[i] = __ballot_sync(FULL, state == 0);
+                if (ip == LW) {
+                    if (pmask[i]) {
+                        ip = i;
+                        below = (pmask[i] & (0u - pmask[i])) - 1u;
+                        ready = ready && ((zmask[i] & below) == 0);
+                    } else {
+                        ready = ready && (zmask[i] == 0);
+                    }
+                }
+            }
 #ifdef BLT_TRACE
             ++dbg_polls;
 #endif
-            if (__any_sync(FULL, bad)) {  // somebody has not published yet
+            if (!ready) {  // somebody nearer than the nearest PREFIX has not published yet: poll again
 #ifdef BLT_TRACE
                 ++dbg_retries;
 #endif
-                continue;  // plain spin: the L2 round trip of the reload is back-off enough
+                continue;
             }
             uint32_t part_sum = 0;
             bool good = true;
             uint64_t pword = 0;
 #pragma unroll
             for (int i = 0; i < LW; ++i) {
-                const bool nearer = (lane < p_lane) || (lane == p_lane && i < p_sub);
+                const bool nearer = (i < ip) || (i == ip && ((below >> lane) & 1u));
                 if (nearer) {
                     const uint32_t hi = uint32_t(st[i] >> 32);
                     // branch `hyp` known (bit 61 - hyp) and its carry_out (bit 59 - hyp) equals hyp
@@ -240,12 +252,13 @@ __device__ __noinline__ bool decoupled_lookback(const uint64_t *status, long lon
                     good = good && known && (cout == hyp);
                     part_sum += uint32_t(st[i] >> (24 * hyp)) & 0xFFFFFFu;
                 }
-                if (lane == p_lane && i == p_sub) pword = st[i];
+                if (i == ip && ((below + 1u) >> lane) == 1u) pword = st[i];  // the PREFIX lane itself
             }
             if (!__all_sync(FULL, good)) break;  // not a pure `hyp` chain: general fold
             sum += __reduce_add_sync(FULL, part_sum);
-            if (p_lane < 32) {
-                pword = __shfl_sync(FULL, pword, p_lane);
+            if (ip < LW) {
+                const int plane = __ffs(below + 1u) - 1;
+                pword = __shfl_sync(FULL, pword, plane);
                 if ((uint32_t(pword >> 59) & 1u) != hyp) break;  // chain is fine but starts from the other carry
                 *carry_in = hyp;
                 *base = (pword & PREFIX_CNT_MASK) + sum;

@@ -16,6 +16,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <chrono>
 #include <thread>
 #include <unistd.h>
 
@@ -121,7 +122,8 @@ namespace {
 //                          bytes must land (see users)
 // Chunk order is preserved by construction: completion is processed for k = 0,1,2,... in order.
 struct ChunkSource {
-    size_t n = 0, chunk = 0, first = 0, last = 0;  // chunks [first,last) of an n-byte input
+    size_t n = 0, chunk = 0, first = 0, last = 0;  // units [first,last) of `chunk` bytes of an n-byte input
+    size_t wall = 0;                                 // the reference's chunk size inside a unit (0: unit == chunk)
     size_t len_of(size_t k) const { return std::min(chunk, n - k * chunk); }
 };
 
@@ -138,7 +140,7 @@ int run_slots(blt_strategy *s, Pipe &pipe, const ChunkSource &src, Fetch fetch, 
         CUDA_TRY(cudaEventRecord(sl.ev_h2d, pipe.s_h2d));
         CUDA_TRY(cudaStreamWaitEvent(pipe.s_comp, sl.ev_h2d, 0));
         if (reuse) CUDA_TRY(cudaStreamWaitEvent(pipe.s_comp, sl.ev_d2h, 0));  // d_out free once copied out
-        int rc = run_device(s, pipe.ws, sl.d_in, sl.in_len, 0, sl.d_out, 2 * pipe.cap, nullptr, pipe.s_comp, &sl.res);
+        int rc = run_device(s, pipe.ws, sl.d_in, sl.in_len, src.wall, sl.d_out, 2 * pipe.cap, nullptr, pipe.s_comp, &sl.res);
         if (rc) return rc;
         if (sl.res.kind == DeviceResult::IN_SCRATCH)
             CUDA_TRY(cudaMemcpyAsync(sl.h_ctrl, pipe.ws.scratch.ctrl, 32, cudaMemcpyDeviceToHost, pipe.s_comp));
@@ -189,13 +191,19 @@ int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, in
         return BLT_OK;
     }
     CUDA_TRY(cudaSetDevice(s->ctx->device));
+    // The pipeline moves UNITS of several reference chunks: one H2D, one launch (the kernels keep the
+    // walls at multiples of `chunk`, which is exactly the concatenation of the per-chunk results) and one
+    // D2H per unit.  Fewer, larger PCIe copies; the output bytes are the same.
+    size_t per_unit = 1;
+    while (per_unit < 8 && chunk * (per_unit * 2) <= (size_t(64) << 20) && chunk * per_unit < n) per_unit *= 2;
+    const size_t unit = chunk * per_unit;
     ChunkSource src;
-    src.n = n; src.chunk = chunk; src.first = 0; src.last = (n + chunk - 1) / chunk;
+    src.n = n; src.chunk = unit; src.wall = chunk; src.first = 0; src.last = (n + unit - 1) / unit;
     auto pipe = s->ctx->acquire();
-    int rc = pipe->ensure(chunk, std::min(kSlots, src.last), false);
+    int rc = pipe->ensure(std::min(unit, n), std::min(kSlots, src.last), false);
     if (rc == BLT_OK) {
         rc = run_slots(
-            s, *pipe, src, [&](size_t k, Slot &) { return in + k * chunk; },
+            s, *pipe, src, [&](size_t k, Slot &) { return in + k * unit; },
             [&](size_t, Slot &sl, size_t len) -> int {
                 if (off + len > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
                 CUDA_TRY(cudaMemcpyAsync(out + off, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
@@ -291,8 +299,23 @@ int build_like(blt_ctx *ctx, const blt_strategy *proto, blt_strategy **out) {
 
 using namespace bltc;
 
+namespace {
+// BLT_LOG=1 prints stage timings to stderr (the reference logs through `tracing` + RUST_LOG, main.rs:83-85).
+struct StageLog {
+    bool on = getenv("BLT_LOG") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what, int dev = -1) {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (dev >= 0) std::fprintf(stderr, "[blt %9.2f ms] gpu%d %s\n", ms, dev, what);
+        else std::fprintf(stderr, "[blt %9.2f ms] %s\n", ms, what);
+    }
+};
+}  // namespace
+
 extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     if (!cfg) return fail(BLT_ERR_INVALID_INPUT, "NULL config");
+    StageLog slog;
     // ---- CoreConfig::new_from_cli (lib.rs:149-174): threads, chunk size, merges, in this order ----
     const size_t threads = blth::determine_thread_count(cfg->has_threads != 0, cfg->threads);
     bool has_cli_chunk = false;
@@ -385,8 +408,10 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         return rc;
     }
 
+    slog.mark("config parsed, io open");
     int n_dev = 0;
     int rc = blt_device_count(&n_dev);
+    slog.mark("device count");
     if (rc) { cleanup(); return rc; }  // no CPU fallback
     int n_gpus = cfg->num_gpus > 0 ? std::min(cfg->num_gpus, n_dev) : n_dev;
     if (!of.seekable) n_gpus = 1;  // a stream can only be written front to back
@@ -450,7 +475,9 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         blt_strategy *st = nullptr;
         std::unique_ptr<Pipe> pipe;
         int rc = blt_ctx_create(sh.device, &ctx);
+        slog.mark("context created", sh.device);
         if (rc == BLT_OK) rc = build_like(ctx, &proto, &st);
+        slog.mark("strategy built", sh.device);
         // Fixed-ratio output (Basic): every shard knows its offset up front and streams with pwrite.
         int64_t base = (mode == Mode::Basic) ? int64_t(2 * sh.first * chunk) : (g == 0 ? 0 : -1);
         uint64_t produced = 0;
@@ -459,6 +486,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
             src.n = n; src.chunk = chunk; src.first = sh.first; src.last = sh.last;
             pipe = ctx->acquire();
             rc = pipe->ensure(std::min(chunk, n), std::min(kSlots, src.last - src.first), true);
+            slog.mark("pipe buffers allocated", sh.device);
             // Output is delivered one chunk late so chunk k's D2H overlaps chunk k+1's host-side input staging.
             struct Pending { Slot *sl = nullptr; size_t len = 0; } pend;
             auto flush = [&](Pending &p) -> int {
@@ -499,6 +527,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
             }
         }
         sh.total = produced;
+        slog.mark("pipeline drained", sh.device);
         if (rc != BLT_OK) { sh.rc = rc; sh.err = blt_last_error(); }
         board.publish(g, int64_t(produced), rc == BLT_OK);
         if (rc == BLT_OK && !sh.held.empty()) {  // wait for the shards before us, then write our range
@@ -508,9 +537,11 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
                 if (rc) { sh.rc = rc; sh.err = blt_last_error(); }
             }
         }
+        slog.mark("held output written", sh.device);
         if (pipe) { pipe->release(); }
         if (st) blt_strategy_destroy(st);
         if (ctx) blt_ctx_destroy(ctx);
+        slog.mark("released", sh.device);
     };
 
     std::vector<std::thread> pool;
@@ -521,6 +552,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         pool.emplace_back(worker, g);
     }
     for (auto &t : pool) t.join();
+    slog.mark("all shards done");
     rc = BLT_OK;
     for (const auto &sh : shards)
         if (sh.rc != BLT_OK && rc == BLT_OK) { rc = sh.rc; fail(sh.rc, sh.err); }  // first error in chunk order

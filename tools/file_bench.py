@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""File-to-file benchmark (BASELINE.json configs[4] shape): synthetic corpus on tmpfs, 60 000-line
+merges.txt, `blt` CLI with the pinned mmap -> H2D -> kernel -> D2H -> pwrite pipeline over G GPUs.
+Prints one JSON line per GPU count; --check compares the output file with the CPU oracle's."""
+import argparse, hashlib, json, os, subprocess, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from blt_b200 import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--bytes", type=int, default=2 << 30)
+ap.add_argument("--gpus", default="1")
+ap.add_argument("--merges", type=int, default=60000)
+ap.add_argument("--dir", default="/dev/shm")
+ap.add_argument("--check", action="store_true")
+ap.add_argument("--mode", default="bpe", choices=["bpe", "basic"])
+args = ap.parse_args()
+blt = os.path.join(ROOT, "blt_b200", "lib", "blt")
+inp, outp, mp = (os.path.join(args.dir, f) for f in ("blt_in.bin", "blt_out.bin", "blt_merges.txt"))
+t0 = time.perf_counter()
+data = synth.text(args.bytes, synth.SEED_CONFIG[5])
+l, r = synth.merges_from_sample(data, args.merges)
+synth.write_merges_file(mp, l, r)
+data.tofile(inp)
+print(f"generated {args.bytes >> 20} MiB in {time.perf_counter() - t0:.1f}s", file=sys.stderr)
+want = None
+if args.check:
+    from oracle import oracle_ffi as ora
+    ref = os.path.join(args.dir, "blt_ref.bin")
+    t0 = time.perf_counter()
+    ora.run_files(args.mode, inp, ref, 16 << 20, os.cpu_count() or 4, ora.Merges.from_file(mp) if args.mode == "bpe" else None)
+    cpu_s = time.perf_counter() - t0
+    want = hashlib.sha256(open(ref, "rb").read()).hexdigest()
+    print(json.dumps({"impl": "oracle file-to-file", "cores": os.cpu_count(), "seconds": round(cpu_s, 2),
+                      "input_GBps": round(args.bytes / cpu_s / 1e9, 3)}), flush=True)
+    os.unlink(ref)
+for g in [int(x) for x in args.gpus.split(",")]:
+    cmd = [blt, "-i", inp, "-o", outp, "--chunksize", "16MB", "--gpus", str(g)] + (["--merges", mp] if args.mode == "bpe" else [])
+    best = None
+    for rep in range(3):
+        t0 = time.perf_counter()
+        subprocess.run(cmd, check=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    line = {"mode": args.mode, "gpus": g, "bytes": args.bytes, "out_bytes": os.path.getsize(outp), "best_seconds": round(best, 3),
+            "input_GBps": round(args.bytes / best / 1e9, 2), "note": "wall clock of the whole `blt` process (context creation, table upload, pipeline, pwrite), tmpfs"}
+    if want is not None:
+        line["matches_oracle"] = hashlib.sha256(open(outp, "rb").read()).hexdigest() == want
+    print(json.dumps(line), flush=True)
+for p in (inp, outp, mp):
+    if os.path.exists(p):
+        os.unlink(p)
