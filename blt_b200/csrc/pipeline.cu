@@ -12,8 +12,10 @@
 #include <cerrno>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
+#include <functional>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <chrono>
@@ -122,20 +124,23 @@ namespace {
 //                          bytes must land (see users)
 // Chunk order is preserved by construction: completion is processed for k = 0,1,2,... in order.
 struct ChunkSource {
-    size_t n = 0, chunk = 0, first = 0, last = 0;  // units [first,last) of `chunk` bytes of an n-byte input
-    size_t wall = 0;                                 // the reference's chunk size inside a unit (0: unit == chunk)
-    size_t len_of(size_t k) const { return std::min(chunk, n - k * chunk); }
+    size_t n = 0, chunk = 0;           // units of `chunk` bytes of an n-byte input
+    size_t first = 0, count = 0, stride = 1;  // this pipeline owns units first, first+stride, ... (count of them)
+    size_t wall = 0;                   // the reference's chunk size inside a unit (0: unit == chunk)
+    size_t id_of(size_t i) const { return first + i * stride; }
+    size_t len_of(size_t id) const { return std::min(chunk, n - id * chunk); }
 };
 
 template <class Fetch, class Sink>
 int run_slots(blt_strategy *s, Pipe &pipe, const ChunkSource &src, Fetch fetch, Sink sink) {
-    const size_t S = std::min(kSlots, src.last - src.first);
-    auto issue = [&](size_t k) -> int {
-        Slot &sl = pipe.slots[(k - src.first) % S];
-        sl.in_len = src.len_of(k);
-        const bool reuse = (k - src.first) >= S;
+    const size_t S = std::min(kSlots, src.count);
+    auto issue = [&](size_t i) -> int {
+        Slot &sl = pipe.slots[i % S];
+        const size_t id = src.id_of(i);
+        sl.in_len = src.len_of(id);
+        const bool reuse = i >= S;
         if (reuse) CUDA_TRY(cudaStreamWaitEvent(pipe.s_h2d, sl.ev_done, 0));   // d_in free once its kernel ran
-        const uint8_t *h = fetch(k, sl);
+        const uint8_t *h = fetch(id, sl);
         CUDA_TRY(cudaMemcpyAsync(sl.d_in, h, sl.in_len, cudaMemcpyHostToDevice, pipe.s_h2d));
         CUDA_TRY(cudaEventRecord(sl.ev_h2d, pipe.s_h2d));
         CUDA_TRY(cudaStreamWaitEvent(pipe.s_comp, sl.ev_h2d, 0));
@@ -147,21 +152,21 @@ int run_slots(blt_strategy *s, Pipe &pipe, const ChunkSource &src, Fetch fetch, 
         CUDA_TRY(cudaEventRecord(sl.ev_done, pipe.s_comp));
         return BLT_OK;
     };
-    for (size_t k = src.first; k < src.first + S; ++k) {
-        int rc = issue(k);
+    for (size_t i = 0; i < S; ++i) {
+        int rc = issue(i);
         if (rc) return rc;
     }
-    for (size_t k = src.first; k < src.last; ++k) {
-        Slot &sl = pipe.slots[(k - src.first) % S];
+    for (size_t i = 0; i < src.count; ++i) {
+        Slot &sl = pipe.slots[i % S];
         CUDA_TRY(cudaEventSynchronize(sl.ev_done));
         if (sl.res.kind == DeviceResult::IN_SCRATCH) {
             int rc = decode_ctrl(sl.h_ctrl, &sl.res);
             if (rc) return rc;
         }
-        int rc = sink(k, sl, sl.res.len);  // enqueues the D2H copy on s_d2h and records ev_d2h
+        int rc = sink(src.id_of(i), sl, sl.res.len);  // enqueues the D2H copy on s_d2h and records ev_d2h
         if (rc) return rc;
-        if (k + S < src.last) {
-            rc = issue(k + S);
+        if (i + S < src.count) {
+            rc = issue(i + S);
             if (rc) return rc;
         }
     }
@@ -198,9 +203,9 @@ int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, in
     while (per_unit < 8 && chunk * (per_unit * 2) <= (size_t(64) << 20) && chunk * per_unit < n) per_unit *= 2;
     const size_t unit = chunk * per_unit;
     ChunkSource src;
-    src.n = n; src.chunk = unit; src.wall = chunk; src.first = 0; src.last = (n + unit - 1) / unit;
+    src.n = n; src.chunk = unit; src.wall = chunk; src.first = 0; src.count = (n + unit - 1) / unit; src.stride = 1;
     auto pipe = s->ctx->acquire();
-    int rc = pipe->ensure(std::min(unit, n), std::min(kSlots, src.last), false);
+    int rc = pipe->ensure(std::min(unit, n), std::min(kSlots, src.count), false);
     if (rc == BLT_OK) {
         rc = run_slots(
             s, *pipe, src, [&](size_t k, Slot &) { return in + k * unit; },
@@ -230,7 +235,14 @@ namespace {
 struct OutFile {
     int fd = -1;
     bool seekable = false;
-    int write_at(const uint8_t *p, size_t n, uint64_t off) {  // pwrite loop
+    uint8_t *map = nullptr;  // regular files: the output is mapped at its upper-bound size and trimmed at the end
+    size_t map_len = 0;      // (pwrite()s from several threads would serialise on the inode lock)
+    int write_at(const uint8_t *p, size_t n, uint64_t off) {  // memcpy into the mapping, else a pwrite loop
+        if (map) {
+            if (off + n > map_len) return fail(BLT_ERR_CAPACITY, "output exceeds its upper bound");
+            std::memcpy(map + off, p, n);
+            return BLT_OK;
+        }
         while (n) {
             const ssize_t w = seekable ? pwrite(fd, p, n, off_t(off)) : write(fd, p, n);
             if (w < 0) {
@@ -243,42 +255,105 @@ struct OutFile {
     }
 };
 
+// A blocking parallel-for over a few helper threads: the host-side copies of the file pipeline (page
+// cache -> pinned staging, pinned staging -> output file) are memory-bound single-threaded otherwise.
+// The reference spreads the same work over its tokio workers (`--threads`, utils.rs:79-97).
+class HostPool {
+  public:
+    explicit HostPool(size_t helpers) {
+        for (size_t i = 0; i < helpers; ++i) threads_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    size_t width() const { return threads_.size() + 1; }
+    // runs fn(0..parts-1); the caller takes part in the work; returns when every part is done
+    template <class F>
+    void run(size_t parts, F fn) {
+        if (parts <= 1 || threads_.empty()) { for (size_t i = 0; i < parts; ++i) fn(i); return; }
+        std::function<void(size_t)> f = fn;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &f; next_ = 0; parts_ = parts; pending_ = parts;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void work() {
+        for (;;) {
+            size_t i;
+            const std::function<void(size_t)> *f;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= parts_) return;
+                i = next_++;
+                f = fn_;
+            }
+            (*f)(i);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop() {
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || (fn_ && next_ < parts_); });
+                if (stop_) return;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t next_ = 0, parts_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
+
 struct GpuShard {
     int device = 0;
-    size_t first = 0, last = 0;      // chunk range
-    std::vector<uint8_t> held;       // output produced before this shard's file offset was known
-    uint64_t total = 0;
+    uint64_t total = 0;  // output bytes this GPU produced
     int rc = BLT_OK;
     std::string err;
 };
 
-// Shared between the per-GPU threads: totals of finished shards -> file offsets of later ones.
+// The only thing the per-GPU pipelines share: the output length of every chunk.  Chunk k's file
+// offset is the sum of the lengths of chunks 0..k-1 (the reference's ordered writer, pipeline.rs:153-168,
+// as a prefix); a pipeline that has chunk k's bytes ready waits here until that sum is known.
 struct OffsetBoard {
     std::mutex mu;
     std::condition_variable cv;
-    std::vector<int64_t> total;  // -1 until shard g has produced all its output
+    std::vector<int64_t> len;   // -1 until chunk k's output length is known
+    std::vector<uint64_t> cum;  // cum[k] = output bytes of chunks 0..k-1, valid for k <= cursor
+    size_t cursor = 0;
     bool failed = false;
-    // Offset of shard g relative to shard 0, or -1 if an earlier shard is still running.
-    int64_t try_base(size_t g) {
-        std::lock_guard<std::mutex> lk(mu);
-        int64_t b = 0;
-        for (size_t i = 0; i < g; ++i) { if (total[i] < 0) return -1; b += total[i]; }
-        return b;
-    }
-    int64_t wait_base(size_t g) {
-        std::unique_lock<std::mutex> lk(mu);
-        int64_t b = 0;
-        cv.wait(lk, [&] {
-            if (failed) return true;
-            b = 0;
-            for (size_t i = 0; i < g; ++i) { if (total[i] < 0) return false; b += total[i]; }
-            return true;
-        });
-        return failed ? -1 : b;
-    }
-    void publish(size_t g, int64_t t, bool ok) {
-        { std::lock_guard<std::mutex> lk(mu); total[g] = t; if (!ok) failed = true; }
+    void init(size_t n_chunks) { len.assign(n_chunks, -1); cum.assign(n_chunks + 1, 0); }
+    void publish(size_t k, uint64_t n) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            len[k] = int64_t(n);
+            while (cursor < len.size() && len[cursor] >= 0) { cum[cursor + 1] = cum[cursor] + uint64_t(len[cursor]); ++cursor; }
+        }
         cv.notify_all();
+    }
+    void fail_all() {
+        { std::lock_guard<std::mutex> lk(mu); failed = true; }
+        cv.notify_all();
+    }
+    // Blocks until every earlier chunk's length is known; -1 if some pipeline failed.
+    int64_t base_of(size_t k) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return failed || cursor >= k; });
+        return failed ? -1 : int64_t(cum[k]);
     }
 };
 
@@ -456,18 +531,30 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     // ---- mmap path: run_mmap_pipeline (pipeline.rs:56-131) over n_gpus devices ----
     const size_t n_chunks = n ? (n + chunk - 1) / chunk : 0;
     if (n_chunks == 0) { cleanup(); return BLT_OK; }  // empty file -> empty output (pipeline.rs:103-105)
+    if (of.seekable && getenv("BLT_NO_MMAP_OUT") == nullptr) {
+        struct stat ost;
+        const size_t bound = size_t(prefix) + 2 * n;
+        if (fstat(of.fd, &ost) == 0 && S_ISREG(ost.st_mode) && ftruncate(of.fd, off_t(bound)) == 0) {
+            // O_WRONLY descriptors cannot be mapped shared: reopen read-write through /proc
+            const std::string self = "/proc/self/fd/" + std::to_string(of.fd);
+            const int rw = open(self.c_str(), O_RDWR);
+            if (rw >= 0) {
+                void *m = mmap(nullptr, bound, PROT_READ | PROT_WRITE, MAP_SHARED, rw, 0);
+                close(rw);
+                if (m != MAP_FAILED) { of.map = static_cast<uint8_t *>(m); of.map_len = bound; }
+            }
+            if (!of.map) (void)!ftruncate(of.fd, off_t(prefix));
+        }
+    }
     if (size_t(n_gpus) > n_chunks) n_gpus = int(n_chunks);
-    std::vector<size_t> bounds(size_t(n_gpus) + 1);
-    blt_shard_chunks(n_chunks, n_gpus, bounds.data());
+    // Chunk k goes to GPU k % G: the pipelines advance through the file together, so a chunk's offset (the
+    // lengths of all earlier chunks) is known almost as soon as its own bytes are back on the host.
     std::vector<GpuShard> shards(static_cast<size_t>(n_gpus));
     OffsetBoard board;
-    board.total.assign(size_t(n_gpus), -1);
+    board.init(n_chunks);
     blt_strategy proto;
     proto.mode = mode;
     proto.rules = rules;
-    if (mode == Mode::BpePairs)
-        for (const auto &r : rules)
-            if (r.value < 256) proto.mode = Mode::BpeGeneral;  // cannot happen for a merges.txt; kept for symmetry
 
     auto worker = [&](size_t g) {
         GpuShard &sh = shards[g];
@@ -478,49 +565,63 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         slog.mark("context created", sh.device);
         if (rc == BLT_OK) rc = build_like(ctx, &proto, &st);
         slog.mark("strategy built", sh.device);
-        // Fixed-ratio output (Basic): every shard knows its offset up front and streams with pwrite.
-        int64_t base = (mode == Mode::Basic) ? int64_t(2 * sh.first * chunk) : (g == 0 ? 0 : -1);
+        // host copies are split over `--threads / gpus` threads (at most 8), like the reference's workers
+        HostPool io(std::min<size_t>(8, std::max<size_t>(1, threads / size_t(n_gpus))) - 1);
+        constexpr size_t kPiece = size_t(2) << 20;
+        auto par_memcpy = [&](uint8_t *dst, const uint8_t *src_p, size_t len) {
+            const size_t parts = std::min(io.width(), (len + kPiece - 1) / kPiece);
+            if (parts <= 1) { std::memcpy(dst, src_p, len); return; }
+            const size_t per = ((len + parts - 1) / parts + 4095) & ~size_t(4095);
+            io.run(parts, [&](size_t i) {
+                const size_t lo = i * per;
+                if (lo < len) std::memcpy(dst + lo, src_p + lo, std::min(per, len - lo));
+            });
+        };
+        auto put = [&](const uint8_t *buf, size_t len, uint64_t off) -> int {
+            if (of.map) {  // mapped output: plain stores, split over the helper threads
+                if (off + len > of.map_len) return fail(BLT_ERR_CAPACITY, "output exceeds its upper bound");
+                par_memcpy(of.map + off, buf, len);
+                return BLT_OK;
+            }
+            return of.write_at(buf, len, off);
+        };
         uint64_t produced = 0;
         if (rc == BLT_OK) {
             ChunkSource src;
-            src.n = n; src.chunk = chunk; src.first = sh.first; src.last = sh.last;
+            src.n = n; src.chunk = chunk; src.first = g; src.stride = size_t(n_gpus);
+            src.count = (n_chunks > g) ? (n_chunks - g + size_t(n_gpus) - 1) / size_t(n_gpus) : 0;
             pipe = ctx->acquire();
-            rc = pipe->ensure(std::min(chunk, n), std::min(kSlots, src.last - src.first), true);
+            rc = pipe->ensure(std::min(chunk, n), std::min(kSlots, std::max<size_t>(src.count, 1)), true);
             slog.mark("pipe buffers allocated", sh.device);
             // Output is delivered one chunk late so chunk k's D2H overlaps chunk k+1's host-side input staging.
-            struct Pending { Slot *sl = nullptr; size_t len = 0; } pend;
+            struct Pending { Slot *sl = nullptr; size_t len = 0, id = 0; } pend;
             auto flush = [&](Pending &p) -> int {
                 if (!p.sl) return BLT_OK;
                 CUDA_TRY(cudaEventSynchronize(p.sl->ev_d2h));
-                if (base < 0) base = board.try_base(g);
-                int w = BLT_OK;
-                if (base >= 0) {
-                    if (!sh.held.empty()) {  // offset just became known: drain what was held back
-                        w = of.write_at(sh.held.data(), sh.held.size(), prefix + uint64_t(base));
-                        std::vector<uint8_t>().swap(sh.held);
-                    }
-                    if (w == BLT_OK) w = of.write_at(p.sl->h_out, p.len, prefix + uint64_t(base) + produced);
-                } else {
-                    sh.held.insert(sh.held.end(), p.sl->h_out, p.sl->h_out + p.len);
-                }
+                // Basic is fixed-ratio: the offset is known up front; otherwise ask the board
+                const int64_t base = (mode == Mode::Basic) ? int64_t(2 * p.id * chunk) : board.base_of(p.id);
+                if (base < 0) return fail(BLT_ERR_IO, "another GPU pipeline failed");
+                const int w = put(p.sl->h_out, p.len, prefix + uint64_t(base));
                 produced += p.len;
                 p.sl = nullptr;
                 return w;
             };
-            if (rc == BLT_OK) {
+            if (rc == BLT_OK && src.count) {
                 rc = run_slots(
                     st, *pipe, src,
-                    [&](size_t k, Slot &sl) {
-                        std::memcpy(sl.h_in, map + k * chunk, src.len_of(k));  // page cache -> pinned
+                    [&](size_t id, Slot &sl) {
+                        par_memcpy(sl.h_in, map + id * chunk, src.len_of(id));  // page cache -> pinned
                         return static_cast<const uint8_t *>(sl.h_in);
                     },
-                    [&](size_t, Slot &sl, size_t len) -> int {
-                        int w = flush(pend);  // previous chunk: its copy has had a full stage to finish
+                    [&](size_t id, Slot &sl, size_t len) -> int {
+                        board.publish(id, len);  // the length is known before the bytes are back
+                        int w = flush(pend);     // previous chunk: its copy has had a full stage to finish
                         if (w) return w;
                         CUDA_TRY(cudaMemcpyAsync(sl.h_out, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
                         CUDA_TRY(cudaEventRecord(sl.ev_d2h, pipe->s_d2h));
                         pend.sl = &sl;
                         pend.len = len;
+                        pend.id = id;
                         return BLT_OK;
                     });
                 if (rc == BLT_OK) rc = flush(pend);
@@ -528,16 +629,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         }
         sh.total = produced;
         slog.mark("pipeline drained", sh.device);
-        if (rc != BLT_OK) { sh.rc = rc; sh.err = blt_last_error(); }
-        board.publish(g, int64_t(produced), rc == BLT_OK);
-        if (rc == BLT_OK && !sh.held.empty()) {  // wait for the shards before us, then write our range
-            const int64_t b = board.wait_base(g);
-            if (b >= 0) {
-                rc = of.write_at(sh.held.data(), sh.held.size(), prefix + uint64_t(b));
-                if (rc) { sh.rc = rc; sh.err = blt_last_error(); }
-            }
-        }
-        slog.mark("held output written", sh.device);
+        if (rc != BLT_OK) { sh.rc = rc; sh.err = blt_last_error(); board.fail_all(); }
         if (pipe) { pipe->release(); }
         if (st) blt_strategy_destroy(st);
         if (ctx) blt_ctx_destroy(ctx);
@@ -547,8 +639,6 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     std::vector<std::thread> pool;
     for (size_t g = 0; g < size_t(n_gpus); ++g) {
         shards[g].device = int(g);
-        shards[g].first = bounds[g];
-        shards[g].last = bounds[g + 1];
         pool.emplace_back(worker, g);
     }
     for (auto &t : pool) t.join();
@@ -556,6 +646,14 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     rc = BLT_OK;
     for (const auto &sh : shards)
         if (sh.rc != BLT_OK && rc == BLT_OK) { rc = sh.rc; fail(sh.rc, sh.err); }  // first error in chunk order
+    if (of.map) {  // trim the mapping's upper bound down to what was produced
+        uint64_t total = prefix;
+        for (const auto &sh : shards) total += sh.total;
+        munmap(of.map, of.map_len);
+        of.map = nullptr;
+        if (ftruncate(of.fd, off_t(total)) != 0 && rc == BLT_OK) rc = fail(BLT_ERR_IO, "ftruncate failed");
+        slog.mark("output trimmed");
+    }
     cleanup();
     return rc;
 }
