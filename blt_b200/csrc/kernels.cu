@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 namespace bltk {
 namespace {
@@ -620,6 +621,8 @@ __device__ __forceinline__ Walls<SEG> seg_walls(const SweepArgs &a, const TileIn
     return w;
 }
 
+#include "sweep3.cuh"
+
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -1111,7 +1114,7 @@ cudaError_t debug_set_trace(unsigned long long *d_buf, unsigned int iters) {
 // ---- scratch -------------------------------------------------------------------------------------
 size_t sweep_scratch_bytes(size_t n_elems_max) {
     const size_t tiles = (n_elems_max + kMinTileElems - 1) / kMinTileElems + 1;
-    return kCtrlBytes + tiles * 8;
+    return kCtrlBytes + tiles * 8 + tiles * 4;
 }
 SweepScratch sweep_scratch_carve(void *mem, size_t n_elems_max) {
     SweepScratch s;
@@ -1127,7 +1130,8 @@ SweepScratch sweep_scratch_carve(void *mem, size_t n_elems_max) {
     s.phase_hint = reinterpret_cast<uint32_t *>(p + 256);
     s.dense_abort = reinterpret_cast<uint32_t *>(p + 384);
     s.tile_status = reinterpret_cast<uint64_t *>(p + kCtrlBytes);
-    s.bytes = kCtrlBytes + tiles * 8;
+    s.tile_desc = reinterpret_cast<uint32_t *>(p + kCtrlBytes + tiles * 8);
+    s.bytes = kCtrlBytes + tiles * 8 + tiles * 4;
     s.max_tiles = tiles;
     return s;
 }
@@ -1196,6 +1200,13 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a_in, const uint16_t *d_tabl
         if (err != cudaSuccess) return err;
         a.dense_flag = a.scratch.dense_abort;
     }
+    static const bool use_lookback = (getenv("BLT_SWEEP_IMPL") != nullptr && std::string(getenv("BLT_SWEEP_IMPL")) == "lookback");
+    if (!use_lookback) {
+        switch (variant) {
+            case 1: return launch_sweep3<PairsFE, 8>(a, p, stream);
+            default: return launch_sweep3<PairsFE, 4>(a, p, stream);
+        }
+    }
     switch (variant) {
         case 1: return launch_sweep<1024, 1, PairsFE>(a, p, stream);
         case 2: return launch_sweep<512, 2, PairsFE>(a, p, stream);
@@ -1209,10 +1220,10 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a_in, const uint16_t *d_tabl
 cudaError_t launch_bpe_sweep_hash(const SweepArgs &a, const HashTableView &t, bool in_is_u16, cudaStream_t stream) {
     if (in_is_u16) {
         HashFE<true>::Params p{t};
-        return launch_sweep<256, 2, HashFE<true>>(a, p, stream);
+        return launch_sweep3<HashFE<true>, 8>(a, p, stream);
     }
     HashFE<false>::Params p{t};
-    return launch_sweep<256, 2, HashFE<false>>(a, p, stream);
+    return launch_sweep3<HashFE<false>, 4>(a, p, stream);
 }
 
 }  // namespace bltk

@@ -51,7 +51,8 @@ struct SweepScratch {
     uint32_t *tile_counter;  // ctrl+128: dynamic tile id dispenser (own 128-byte line)
     uint32_t *phase_hint;    // ctrl+256: (unused since tiles are assigned statically)
     uint32_t *dense_abort;   // ctrl+384: set by the dense kernel when its speculation fails (own line)
-    uint64_t *tile_status;   // ctrl+512: one word per tile (look-back descriptors)
+    uint64_t *tile_status;   // ctrl+512: one word per tile (look-back descriptors / scan results)
+    uint32_t *tile_desc;     // after tile_status: one word per tile (carry function + token count)
     size_t bytes;            // size of the whole region
     size_t max_tiles;
 };

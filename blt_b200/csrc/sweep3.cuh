@@ -1,0 +1,438 @@
+// sweep3.cuh -- the exact sweep as three launches without any inter-CTA waiting:
+//
+//   count_kernel  every warp reads its tiles (R rounds x 32 lanes x 16 bytes), looks all pairs up and
+//                 reduces each tile to its carry function: identity or constant carry_out, tokens
+//                 emitted if carry_in = 0, and the 0/1-token `delta` for carry_in = 1.  4 bytes per tile.
+//   scan_kernel   one CTA composes those functions in order and stores, per tile, the carry entering
+//                 it and the number of tokens emitted before it (chunk walls need nothing special: a
+//                 wall makes the tile's function constant).
+//   emit_kernel   every warp re-reads its tiles knowing carry_in and base.  It looks up the pairs of the
+//                 carry's parity first; where all 32 lanes find theirs the warp-round is dense and its
+//                 tokens go out with one 16-byte store per lane straight from registers; otherwise the
+//                 other parity is looked up and the round is compacted through a warp-private
+//                 shared-memory staging line.
+//
+// Everything is warp-synchronous (no block barrier after the table load, no spinning, no cooperative
+// launch); the price is that the input is read twice (2*N_in + 2*T_out bytes of DRAM traffic).
+// Included by kernels.cu inside its anonymous namespace, after the front ends and seg_walls().
+#pragma once
+
+constexpr uint32_t D_ID = 1u << 31, D_CONST = 1u << 30, D_DELTA = 1u << 29, D_CNT = (1u << 24) - 1;
+constexpr uint64_t R_CARRY = 1ull << 63;
+
+template <class FE, int R>
+struct Sweep3Cfg {
+    static constexpr int SEG = FE::SEG;
+    static constexpr int HV = SEG / 4;
+    static constexpr int ROUND_ELEMS = 32 * SEG;
+    static constexpr int TILE_ELEMS = R * ROUND_ELEMS;
+    static constexpr uint32_t ALL = (1u << SEG) - 1;
+    static constexpr uint32_t EVEN = 0x55555555u & ALL;
+    static constexpr uint32_t HALF_ALL = (1u << (SEG / 2)) - 1;
+    static constexpr int STAGE_TOKENS = ROUND_ELEMS + 8;  // per warp
+};
+
+// Per-warp walk over its tiles: tile = first + k * n_warps, with the chunk bookkeeping kept incrementally.
+template <int TILE_ELEMS>
+struct TileWalk {
+    long long tile, n_tiles, n_warps;
+    unsigned long long stride_elems;
+    TileInfo ti;
+    __device__ __forceinline__ void init(const SweepArgs &a, long long first, long long warps) {
+        n_tiles = (long long)((a.n + TILE_ELEMS - 1) / TILE_ELEMS);
+        n_warps = warps;
+        stride_elems = (unsigned long long)warps * TILE_ELEMS;
+        tile = first;
+        ti.rem0 = (unsigned long long)first * TILE_ELEMS;
+        ti.ck0 = 0;
+        if (a.chunk != 0) { ti.ck0 = ti.rem0 / a.chunk; ti.rem0 -= ti.ck0 * a.chunk; }
+    }
+    __device__ __forceinline__ void next(const SweepArgs &a) {
+        tile += n_warps;
+        ti.rem0 += stride_elems;
+        if (a.chunk != 0 && ti.rem0 >= a.chunk) {
+            const unsigned long long q = ti.rem0 / a.chunk;
+            ti.ck0 += q;
+            ti.rem0 -= q * a.chunk;
+        }
+    }
+};
+
+// Loads one tile's R segments for this lane (+ the look-ahead element of every segment in lane 31).
+template <class FE, int R>
+__device__ __forceinline__ void load_tile3(const SweepArgs &a, unsigned long long tile_base, int lane, uint4 *w, uint32_t *nx) {
+    using C = Sweep3Cfg<FE, R>;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const unsigned long long g = tile_base + uint32_t(r * C::ROUND_ELEMS + lane * C::SEG);
+        w[r] = make_uint4(0, 0, 0, 0);
+        nx[r] = 0;
+        if (g + C::SEG <= a.n) {
+            w[r] = ldg_stream_v4(static_cast<const unsigned char *>(a.in) + g * FE::ELEM);
+        } else if (g < a.n) {  // ragged last segment: element-wise, never reads past n
+            uint32_t tmp[4] = {0, 0, 0, 0};
+            for (int j = 0; j < C::SEG && g + j < a.n; ++j) {
+                const uint32_t v = FE::load_elem(a.in, g + j);
+                if (FE::ELEM == 1) tmp[j >> 2] |= v << (8 * (j & 3));
+                else tmp[j >> 1] |= __byte_perm(v, 0, 0x4401) << (16 * (j & 1));
+            }
+            w[r] = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
+        if (lane == 31 && g + C::SEG < a.n) nx[r] = FE::load_elem(a.in, g + C::SEG);
+    }
+}
+
+// Membership word of one segment (both parities looked up), with walls and the end of input applied.
+// hv / ov receive the tokens of the even / odd positions (raw token at wall positions).
+template <class FE, int TILE_ELEMS>
+__device__ __forceinline__ uint32_t segment_full(const FE &fe, const SweepArgs &a, const TileInfo &ti, bool simple,
+                                                 bool end_wall_here, uint32_t off, unsigned long long g, const uint4 &w,
+                                                 uint32_t next, uint32_t *hv, uint32_t *ov, uint32_t *valid_out,
+                                                 Walls<FE::SEG> *wl_out) {
+    constexpr int SEG = FE::SEG;
+    constexpr uint32_t ALL = (1u << SEG) - 1;
+    const uint32_t hp = fe.lookup_half(w, next, 0u, hv);
+    const uint32_t op = fe.lookup_half(w, next, 1u, ov);
+    Walls<SEG> wl;
+    wl.endm = 0;
+    wl.ck = ti.ck0;
+    uint32_t valid = ALL;
+    if (simple) {
+        if (end_wall_here) wl.endm = 1u << (SEG - 1);
+    } else {
+        wl = seg_walls<SEG, TILE_ELEMS>(a, ti, off, g);
+        valid = (g + SEG <= a.n) ? ALL : (g < a.n ? ((1u << uint32_t(a.n - g)) - 1) : 0u);
+    }
+    if (wl.endm) {  // a wall suppresses the pair: the raw token is emitted there, not the merged id
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+            if ((wl.endm >> j) & 1u) {
+                const uint32_t be = FE::raw_be(w, j);
+                uint32_t &dst = (j & 1) ? ov[j >> 2] : hv[j >> 2];
+                dst = ((j >> 1) & 1) ? ((dst & 0x0000ffffu) | (be << 16)) : ((dst & 0xffff0000u) | be);
+            }
+        }
+    }
+    *valid_out = valid;
+    *wl_out = wl;
+    return (spread_even(hp) | (spread_even(op) << 1)) & valid & ~wl.endm & ALL;
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <class FE, int R>
+__global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a, const typename FE::Params fp) {
+    using C = Sweep3Cfg<FE, R>;
+    constexpr int SEG = C::SEG;
+    constexpr uint32_t ALL = C::ALL;
+    if (a.dense_flag != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.dense_flag) == 0u) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    FE fe;
+    fe.init(fp, smem);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    TileWalk<C::TILE_ELEMS> tw;
+    tw.init(a, (long long)blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5), (long long)gridDim.x * (kCtaThreads / 32));
+    for (; tw.tile < tw.n_tiles; tw.next(a)) {
+        const unsigned long long tile_base = (unsigned long long)tw.tile * C::TILE_ELEMS;
+        const bool simple = (tile_base + C::TILE_ELEMS < a.n) && (a.chunk == 0 || tw.ti.rem0 + C::TILE_ELEMS <= a.chunk);
+        const bool end_wall = (a.chunk != 0) && (tw.ti.rem0 + C::TILE_ELEMS == a.chunk);
+        uint4 w[R];
+        uint32_t nx[R];
+        load_tile3<FE, R>(a, tile_base, lane, w, nx);
+        bool t_id = true;
+        uint32_t t_const = 0, cnt0 = 0, delta = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t off = uint32_t(r * C::ROUND_ELEMS + lane * SEG);
+            uint32_t next = __shfl_down_sync(FULL, FE::first_elem(w[r]), 1);
+            if (lane == 31) next = nx[r];
+            uint32_t hv[C::HV], ov[C::HV], valid;
+            Walls<SEG> wl;
+            const uint32_t m = segment_full<FE, C::TILE_ELEMS>(fe, a, tw.ti, simple, end_wall && r == R - 1 && lane == 31, off,
+                                                               tile_base + off, w[r], next, hv, ov, &valid, &wl);
+            const uint32_t lead = __clz(~(m << (32 - SEG)));   // ones at the top of the segment
+            const uint32_t nid = ~__ballot_sync(FULL, m == ALL);
+            const uint32_t cob = __ballot_sync(FULL, (lead & 1u) != 0);
+            // carry entering this lane if the tile's carry_in is 0
+            const uint32_t c_round0 = t_id ? 0u : t_const;
+            const uint32_t l_nid = nid & ((1u << lane) - 1);
+            const uint32_t cin0 = l_nid ? ((cob >> (31 - __clz(l_nid))) & 1u) : c_round0;
+            const uint32_t st = start_bits(m, cin0);
+            const uint32_t cnt = __popc(valid & ~((st << 1) | cin0));
+            cnt0 += __reduce_add_sync(FULL, cnt);
+            if (nid) {
+                if (t_id) {  // the first non-identity segment of the tile is the only one whose count sees the tile's carry_in
+                    const int f = __ffs(nid) - 1;
+                    const uint32_t st1 = start_bits(m, 1u);
+                    const uint32_t d = cnt - __popc(valid & ~((st1 << 1) | 1u));
+                    delta = __shfl_sync(FULL, d, f);
+                }
+                t_id = false;
+                t_const = (cob >> (31 - __clz(nid))) & 1u;
+            }
+        }
+        if (lane == 0) a.scratch.tile_desc[tw.tile] = (t_id ? D_ID : 0u) | (t_const ? D_CONST : 0u) | (delta ? D_DELTA : 0u) | cnt0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct ScanFn {
+    uint32_t id, cst, delta;
+    unsigned long long cnt0;
+};
+__device__ __forceinline__ ScanFn scan_decode(uint32_t d) {
+    ScanFn f;
+    f.id = d >> 31; f.cst = (d >> 30) & 1u; f.delta = (d >> 29) & 1u; f.cnt0 = d & D_CNT;
+    return f;
+}
+__device__ __forceinline__ ScanFn scan_compose(const ScanFn &far, const ScanFn &near) {  // carry flows far -> near
+    ScanFn r;
+    const uint32_t c_mid0 = far.id ? 0u : far.cst;
+    r.cnt0 = far.cnt0 + near.cnt0 - ((c_mid0 && near.delta) ? 1u : 0u);
+    r.delta = far.id ? near.delta : far.delta;
+    r.cst = near.id ? far.cst : near.cst;
+    r.id = far.id & near.id;
+    return r;
+}
+__device__ __forceinline__ ScanFn scan_shfl_up(const ScanFn &f, int d) {
+    ScanFn o;
+    const uint32_t packed = f.id | (f.cst << 1) | (f.delta << 2);
+    const uint32_t p = __shfl_up_sync(FULL, packed, d);
+    o.id = p & 1u; o.cst = (p >> 1) & 1u; o.delta = (p >> 2) & 1u;
+    o.cnt0 = __shfl_up_sync(FULL, f.cnt0, d);
+    return o;
+}
+
+constexpr int kScanItems = 8;  // descriptors per thread per block of the scan
+
+// One CTA.  res[t] = (carry entering tile t) << 63 | tokens emitted by tiles 0..t-1.
+__global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a, long long n_tiles) {
+    if (a.dense_flag != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.dense_flag) == 0u) {
+        // the dense pass in front of this launch already produced the whole output: publish its totals
+        const unsigned long long tokens = (a.n + 1) / 2;
+        if (threadIdx.x == 0) {
+            *a.scratch.total_tokens = tokens;
+            *a.scratch.merged_any = (a.n >= 2) ? 1u : 0u;
+        }
+        if (a.chunk_ends != nullptr) {
+            const unsigned long long c = (a.chunk == 0 || a.chunk > a.n) ? a.n : a.chunk;
+            const unsigned long long n_chunks = (a.n + c - 1) / c;
+            for (unsigned long long k = threadIdx.x; k < n_chunks; k += blockDim.x)
+                a.chunk_ends[k] = a.chunk_ends_base + ((k + 1 == n_chunks) ? 2 * tokens : (k + 1) * c);
+        }
+        return;
+    }
+    __shared__ ScanFn warp_agg[32];
+    __shared__ uint32_t blk_carry_s;
+    __shared__ unsigned long long blk_base_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t *desc = a.scratch.tile_desc;
+    uint64_t *res = a.scratch.tile_status;
+    uint32_t blk_carry = 0;             // concrete carry / base at the start of the current block
+    unsigned long long blk_base = 0;
+    for (long long blk = 0; blk < n_tiles; blk += (long long)kCtaThreads * kScanItems) {
+        const long long t0 = blk + (long long)threadIdx.x * kScanItems;
+        uint32_t d[kScanItems];
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) d[i] = (t0 + i < n_tiles) ? desc[t0 + i] : D_ID;  // identity padding
+        ScanFn agg = scan_decode(d[0]);
+#pragma unroll
+        for (int i = 1; i < kScanItems; ++i) agg = scan_compose(agg, scan_decode(d[i]));
+        // inclusive scan of the thread aggregates inside the warp, then across the 32 warps
+        ScanFn inc = agg;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const ScanFn o = scan_shfl_up(inc, s);
+            if (lane >= s) inc = scan_compose(o, inc);
+        }
+        if (lane == 31) warp_agg[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            ScanFn wa = warp_agg[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const ScanFn o = scan_shfl_up(wa, s);
+                if (lane >= s) wa = scan_compose(o, wa);
+            }
+            warp_agg[lane] = wa;  // inclusive over warps
+        }
+        __syncthreads();
+        // exclusive prefix function of this thread = (warps before) o (lanes before)
+        ScanFn ex;
+        ex.id = 1; ex.cst = 0; ex.delta = 0; ex.cnt0 = 0;
+        if (wid > 0) ex = warp_agg[wid - 1];
+        {
+            const ScanFn up = scan_shfl_up(inc, 1);
+            if (lane > 0) ex = scan_compose(ex, up);
+        }
+        uint32_t c = ex.id ? blk_carry : ex.cst;
+        unsigned long long b = blk_base + ex.cnt0 - ((blk_carry && ex.delta) ? 1u : 0u);
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            if (t0 + i < n_tiles) {
+                res[t0 + i] = (c ? R_CARRY : 0ull) | b;
+                b += (d[i] & D_CNT) - ((c && (d[i] & D_DELTA)) ? 1u : 0u);
+                c = (d[i] & D_ID) ? c : ((d[i] >> 30) & 1u);
+            }
+        }
+        if (threadIdx.x == kCtaThreads - 1) { blk_carry_s = c; blk_base_s = b; }
+        __syncthreads();
+        blk_carry = blk_carry_s;
+        blk_base = blk_base_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *a.scratch.total_tokens = blk_base;
+        *a.scratch.merged_any = (blk_base < a.n) ? 1u : 0u;
+        if (a.out_base_tokens + blk_base > a.out_cap_tokens) *a.scratch.overflow = 1u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <class FE, int R>
+__global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a, const typename FE::Params fp) {
+    using C = Sweep3Cfg<FE, R>;
+    constexpr int SEG = C::SEG;
+    constexpr int HV = C::HV;
+    constexpr uint32_t ALL = C::ALL;
+    if (a.dense_flag != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.dense_flag) == 0u) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    FE fe;
+    fe.init(fp, smem);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint16_t *stage = reinterpret_cast<uint16_t *>(smem + FE::TABLE_BYTES) + size_t(threadIdx.x >> 5) * C::STAGE_TOKENS;
+    const uint64_t *res = a.scratch.tile_status;
+    TileWalk<C::TILE_ELEMS> tw;
+    tw.init(a, (long long)blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5), (long long)gridDim.x * (kCtaThreads / 32));
+    for (; tw.tile < tw.n_tiles; tw.next(a)) {
+        const unsigned long long tile_base = (unsigned long long)tw.tile * C::TILE_ELEMS;
+        const bool simple = (tile_base + C::TILE_ELEMS < a.n) && (a.chunk == 0 || tw.ti.rem0 + C::TILE_ELEMS <= a.chunk);
+        const bool end_wall = (a.chunk != 0) && (tw.ti.rem0 + C::TILE_ELEMS == a.chunk);
+        uint4 w[R];
+        uint32_t nx[R];
+        load_tile3<FE, R>(a, tile_base, lane, w, nx);
+        const uint64_t rv = res[tw.tile];
+        uint32_t carry = uint32_t(rv >> 63);
+        unsigned long long rel = rv & ~R_CARRY;  // tokens emitted before this tile (this launch)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t off = uint32_t(r * C::ROUND_ELEMS + lane * SEG);
+            const unsigned long long g = tile_base + off;
+            uint32_t next = __shfl_down_sync(FULL, FE::first_elem(w[r]), 1);
+            if (lane == 31) next = nx[r];
+            const unsigned long long out_pos = rel + a.out_base_tokens;
+            const bool wall_here = end_wall && r == R - 1 && lane == 31;
+            // ---- dense warp-round: the pairs of the carry's parity are all rules ----
+            if (FE::kMembershipInValue && simple && (out_pos % (SEG / 2) == 0)) {
+                uint32_t hv[HV];
+                fe.lookup_vals(w[r], next, carry, hv);
+                const bool ok = FE::all_present(hv) && !(wall_here && carry);
+                if (__all_sync(FULL, ok)) {
+                    if (out_pos + C::ROUND_ELEMS / 2 <= a.out_cap_tokens) {
+                        uint16_t *dst = a.out + out_pos + size_t(lane) * (SEG / 2);
+                        if (SEG == 16) stg_stream_v4(dst, make_uint4(hv[0], hv[1], hv[HV > 2 ? 2 : 0], hv[HV > 3 ? 3 : 0]));
+                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(hv[0], hv[1]);
+                    } else if (lane == 0) {
+                        *a.scratch.overflow = 1u;
+                    }
+                    rel += C::ROUND_ELEMS / 2;
+                    if (wall_here && a.chunk_ends != nullptr) a.chunk_ends[tw.ti.ck0] = a.chunk_ends_base + 2ull * rel;
+                    continue;  // carry is unchanged
+                }
+            }
+            // ---- general warp-round ----
+            uint32_t hv[HV], ov[HV], valid;
+            Walls<SEG> wl;
+            const uint32_t m = segment_full<FE, C::TILE_ELEMS>(fe, a, tw.ti, simple, wall_here, off, g, w[r], next, hv, ov, &valid, &wl);
+            const uint32_t lead = __clz(~(m << (32 - SEG)));
+            const uint32_t nid = ~__ballot_sync(FULL, m == ALL);
+            const uint32_t cob = __ballot_sync(FULL, (lead & 1u) != 0);
+            const uint32_t l_nid = nid & ((1u << lane) - 1);
+            const uint32_t cin = l_nid ? ((cob >> (31 - __clz(l_nid))) & 1u) : carry;
+            const uint32_t st = start_bits(m, cin);
+            const uint32_t em = valid & ~((st << 1) | cin);
+            const uint32_t cnt = __popc(em);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t pos = incl - cnt;
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (a.chunk_ends != nullptr && wl.endm) {
+                uint32_t e = wl.endm;
+                unsigned long long ck = wl.ck;
+                while (e) {
+                    const int d = __ffs(e) - 1;
+                    e &= e - 1;
+                    a.chunk_ends[ck++] = a.chunk_ends_base + 2ull * (rel + pos + __popc(em & ((2u << d) - 1)));
+                }
+            }
+            const uint32_t phase = uint32_t(out_pos & 7);  // keep the 16-byte phase of the output
+            uint32_t sp = phase + pos;
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) {
+                if ((em >> j) & 1u) {
+                    const uint32_t v = (j & 1) ? ov[j >> 2] : hv[j >> 2];
+                    stage[sp++] = uint16_t(((j >> 1) & 1) ? (v >> 16) : v);
+                }
+            }
+            __syncwarp();
+            if (out_pos + total <= a.out_cap_tokens) {
+                uint16_t *dst = a.out + (out_pos - phase);  // 16-byte aligned
+                const uint32_t lo = phase, hi = phase + total;
+                for (uint32_t v = lane; v * 8 < hi; v += 32) {
+                    const uint32_t t0 = v * 8;
+                    if (t0 >= lo && t0 + 8 <= hi) {
+                        stg_stream_v4(dst + t0, *reinterpret_cast<const uint4 *>(stage + t0));
+                    } else {
+                        for (uint32_t k = (t0 > lo ? t0 : lo); k < t0 + 8 && k < hi; ++k) dst[k] = stage[k];
+                    }
+                }
+            } else if (lane == 0) {
+                *a.scratch.overflow = 1u;
+            }
+            __syncwarp();
+            rel += total;
+            if (nid) carry = (cob >> (31 - __clz(nid))) & 1u;
+        }
+    }
+}
+
+template <class FE, int R>
+cudaError_t launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, cudaStream_t stream) {
+    using C = Sweep3Cfg<FE, R>;
+    static_assert(size_t(C::TILE_ELEMS) >= kMinTileElems, "descriptor arrays are sized by kMinTileElems");
+    constexpr size_t smem_count = FE::TABLE_BYTES;
+    constexpr size_t smem_emit = FE::TABLE_BYTES + size_t(kCtaThreads / 32) * C::STAGE_TOKENS * 2;
+    static_assert(smem_emit <= 227 * 1024, "shared memory budget");
+    auto kc = count_kernel<FE, R>;
+    auto ke = emit_kernel<FE, R>;
+    static std::atomic<bool> configured[kMaxDevices];
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (!configured[dev].load(std::memory_order_acquire)) {
+        err = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_count));
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_emit));
+        if (err != cudaSuccess) return err;
+        configured[dev].store(true, std::memory_order_release);
+    }
+    const size_t n_tiles = (a.n + C::TILE_ELEMS - 1) / C::TILE_ELEMS;
+    if (n_tiles + 1 > a.scratch.max_tiles) return cudaErrorInvalidValue;
+    // (the dense-abort word at ctrl+384 belongs to the dense pass enqueued in front of this launch: keep it)
+    err = cudaMemsetAsync(a.scratch.ctrl, 0, 384, stream);
+    if (err != cudaSuccess) return err;
+    const size_t warps_per_cta = kCtaThreads / 32;
+    size_t grid = (n_tiles + warps_per_cta - 1) / warps_per_cta;
+    if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
+    if (grid == 0) grid = 1;
+    kc<<<dim3(unsigned(grid)), dim3(kCtaThreads), smem_count, stream>>>(a, fp);
+    scan_kernel<<<1, kCtaThreads, 0, stream>>>(a, (long long)n_tiles);
+    ke<<<dim3(unsigned(grid)), dim3(kCtaThreads), smem_emit, stream>>>(a, fp);
+    return cudaGetLastError();
+}

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 
 from blt_b200 import _native as nat, synth  # noqa: E402
 
-VARIANT_NAMES = ["g1024r2", "g1024r1", "g512r2", "g256r2", "g512r1", "g256r1"]
+VARIANT_NAMES = ["sweep3 R=4", "sweep3 R=8", "v2", "v3", "v4", "v5"]
 
 
 def time_resident(strat, d_in, n, chunk, d_out, iters):
