@@ -13,6 +13,7 @@
 // same look-back word carries the running output count, so compaction needs no second pass.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -1113,12 +1114,12 @@ cudaError_t debug_set_trace(unsigned long long *d_buf, unsigned int iters) {
 
 // ---- scratch -------------------------------------------------------------------------------------
 size_t sweep_scratch_bytes(size_t n_elems_max) {
-    const size_t tiles = (n_elems_max + kMinTileElems - 1) / kMinTileElems + 1;
+    const size_t tiles = std::max<size_t>((n_elems_max + kMinTileElems - 1) / kMinTileElems + 1, 2 * 8192);
     return kCtrlBytes + tiles * 8 + tiles * 4;
 }
 SweepScratch sweep_scratch_carve(void *mem, size_t n_elems_max) {
     SweepScratch s;
-    const size_t tiles = (n_elems_max + kMinTileElems - 1) / kMinTileElems + 1;
+    const size_t tiles = std::max<size_t>((n_elems_max + kMinTileElems - 1) / kMinTileElems + 1, 2 * 8192);
     unsigned char *p = static_cast<unsigned char *>(mem);
     s.ctrl = p;
     // The tile counter (one atomic per tile from every SM) and the phase hint (read by every claim)

@@ -1,16 +1,18 @@
 // sweep3.cuh -- the exact sweep as three launches without any inter-CTA waiting:
 //
-//   count_kernel  every warp reads its tiles (R rounds x 32 lanes x 16 bytes), looks all pairs up and
-//                 reduces each tile to its carry function: identity or constant carry_out, tokens
-//                 emitted if carry_in = 0, and the 0/1-token `delta` for carry_in = 1.  4 bytes per tile.
-//   scan_kernel   one CTA composes those functions in order and stores, per tile, the carry entering
-//                 it and the number of tokens emitted before it (chunk walls need nothing special: a
-//                 wall makes the tile's function constant).
-//   emit_kernel   every warp re-reads its tiles knowing carry_in and base.  It looks up the pairs of the
-//                 carry's parity first; where all 32 lanes find theirs the warp-round is dense and its
-//                 tokens go out with one 16-byte store per lane straight from registers; otherwise the
-//                 other parity is looked up and the round is compacted through a warp-private
-//                 shared-memory staging line.
+//   count_kernel  every warp owns a CONTIGUOUS range of tiles (a tile = R rounds x 32 lanes x 16 bytes),
+//                 looks all pairs up and reduces its whole range to one carry function: identity or
+//                 constant carry_out, tokens emitted if carry_in = 0, and the 0/1-token `delta` for
+//                 carry_in = 1.
+//   scan_kernel   one CTA composes the (at most 8192) range functions in order and stores, per warp,
+//                 the carry entering its range and the number of tokens emitted before it (chunk walls
+//                 need nothing special: a wall makes a function constant).
+//   emit_kernel   every warp re-reads its range knowing carry_in and base and streams its output.  It
+//                 looks up the pairs of the carry's parity first; where all 32 lanes find theirs the
+//                 warp-round is dense and its tokens go out with one 16-byte store per lane straight
+//                 from registers; otherwise the other parity is looked up and the round is compacted
+//                 into a warp-private shared-memory staging line that only ever flushes whole 16-byte
+//                 vectors (the < 8 leftover tokens stay for the next round).
 //
 // Everything is warp-synchronous (no block barrier after the table load, no spinning, no cooperative
 // launch); the price is that the input is read twice (2*N_in + 2*T_out bytes of DRAM traffic).
@@ -32,24 +34,23 @@ struct Sweep3Cfg {
     static constexpr int STAGE_TOKENS = ROUND_ELEMS + 8;  // per warp
 };
 
-// Per-warp walk over its tiles: tile = first + k * n_warps, with the chunk bookkeeping kept incrementally.
+// Per-warp walk over its contiguous range of tiles, with the chunk bookkeeping kept incrementally.
 template <int TILE_ELEMS>
 struct TileWalk {
-    long long tile, n_tiles, n_warps;
-    unsigned long long stride_elems;
+    long long tile, end;
     TileInfo ti;
-    __device__ __forceinline__ void init(const SweepArgs &a, long long first, long long warps) {
-        n_tiles = (long long)((a.n + TILE_ELEMS - 1) / TILE_ELEMS);
-        n_warps = warps;
-        stride_elems = (unsigned long long)warps * TILE_ELEMS;
-        tile = first;
-        ti.rem0 = (unsigned long long)first * TILE_ELEMS;
+    __device__ __forceinline__ void init(const SweepArgs &a, long long warp, long long n_warps) {
+        const long long n_tiles = (long long)((a.n + TILE_ELEMS - 1) / TILE_ELEMS);
+        const long long per = (n_tiles + n_warps - 1) / n_warps;
+        tile = warp * per;
+        end = tile + per < n_tiles ? tile + per : n_tiles;
+        ti.rem0 = (unsigned long long)tile * TILE_ELEMS;
         ti.ck0 = 0;
-        if (a.chunk != 0) { ti.ck0 = ti.rem0 / a.chunk; ti.rem0 -= ti.ck0 * a.chunk; }
+        if (a.chunk != 0 && tile < end) { ti.ck0 = ti.rem0 / a.chunk; ti.rem0 -= ti.ck0 * a.chunk; }
     }
     __device__ __forceinline__ void next(const SweepArgs &a) {
-        tile += n_warps;
-        ti.rem0 += stride_elems;
+        tile += 1;
+        ti.rem0 += TILE_ELEMS;
         if (a.chunk != 0 && ti.rem0 >= a.chunk) {
             const unsigned long long q = ti.rem0 / a.chunk;
             ti.ck0 += q;
@@ -119,6 +120,8 @@ __device__ __forceinline__ uint32_t segment_full(const FE &fe, const SweepArgs &
 }
 
 // ---------------------------------------------------------------------------------------------------
+constexpr int kMaxRanges = 8192;  // warps of one launch (148 SMs x 32 warps = 4736)
+
 template <class FE, int R>
 __global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a, const typename FE::Params fp) {
     using C = Sweep3Cfg<FE, R>;
@@ -130,17 +133,20 @@ __global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a
     fe.init(fp, smem);
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5);
     TileWalk<C::TILE_ELEMS> tw;
-    tw.init(a, (long long)blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5), (long long)gridDim.x * (kCtaThreads / 32));
-    for (; tw.tile < tw.n_tiles; tw.next(a)) {
+    tw.init(a, warp, (long long)gridDim.x * (kCtaThreads / 32));
+    // the range's carry function, accumulated over all its tiles
+    bool t_id = true;
+    uint32_t t_const = 0, delta = 0;
+    unsigned long long cnt0 = 0;
+    for (; tw.tile < tw.end; tw.next(a)) {
         const unsigned long long tile_base = (unsigned long long)tw.tile * C::TILE_ELEMS;
         const bool simple = (tile_base + C::TILE_ELEMS < a.n) && (a.chunk == 0 || tw.ti.rem0 + C::TILE_ELEMS <= a.chunk);
         const bool end_wall = (a.chunk != 0) && (tw.ti.rem0 + C::TILE_ELEMS == a.chunk);
         uint4 w[R];
         uint32_t nx[R];
         load_tile3<FE, R>(a, tile_base, lane, w, nx);
-        bool t_id = true;
-        uint32_t t_const = 0, cnt0 = 0, delta = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const uint32_t off = uint32_t(r * C::ROUND_ELEMS + lane * SEG);
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a
             const uint32_t lead = __clz(~(m << (32 - SEG)));   // ones at the top of the segment
             const uint32_t nid = ~__ballot_sync(FULL, m == ALL);
             const uint32_t cob = __ballot_sync(FULL, (lead & 1u) != 0);
-            // carry entering this lane if the tile's carry_in is 0
+            // carry entering this lane if the range's carry_in is 0
             const uint32_t c_round0 = t_id ? 0u : t_const;
             const uint32_t l_nid = nid & ((1u << lane) - 1);
             const uint32_t cin0 = l_nid ? ((cob >> (31 - __clz(l_nid))) & 1u) : c_round0;
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a
             const uint32_t cnt = __popc(valid & ~((st << 1) | cin0));
             cnt0 += __reduce_add_sync(FULL, cnt);
             if (nid) {
-                if (t_id) {  // the first non-identity segment of the tile is the only one whose count sees the tile's carry_in
+                if (t_id) {  // the first non-identity segment of the range is the only one whose count sees the range's carry_in
                     const int f = __ffs(nid) - 1;
                     const uint32_t st1 = start_bits(m, 1u);
                     const uint32_t d = cnt - __popc(valid & ~((st1 << 1) | 1u));
@@ -171,7 +177,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a
                 t_const = (cob >> (31 - __clz(nid))) & 1u;
             }
         }
-        if (lane == 0) a.scratch.tile_desc[tw.tile] = (t_id ? D_ID : 0u) | (t_const ? D_CONST : 0u) | (delta ? D_DELTA : 0u) | cnt0;
+    }
+    if (lane == 0 && warp < kMaxRanges) {
+        a.scratch.tile_desc[warp] = (t_id ? D_ID : 0u) | (t_const ? D_CONST : 0u) | (delta ? D_DELTA : 0u);
+        a.scratch.tile_status[kMaxRanges + warp] = cnt0;
     }
 }
 
@@ -180,11 +189,6 @@ struct ScanFn {
     uint32_t id, cst, delta;
     unsigned long long cnt0;
 };
-__device__ __forceinline__ ScanFn scan_decode(uint32_t d) {
-    ScanFn f;
-    f.id = d >> 31; f.cst = (d >> 30) & 1u; f.delta = (d >> 29) & 1u; f.cnt0 = d & D_CNT;
-    return f;
-}
 __device__ __forceinline__ ScanFn scan_compose(const ScanFn &far, const ScanFn &near) {  // carry flows far -> near
     ScanFn r;
     const uint32_t c_mid0 = far.id ? 0u : far.cst;
@@ -203,10 +207,10 @@ __device__ __forceinline__ ScanFn scan_shfl_up(const ScanFn &f, int d) {
     return o;
 }
 
-constexpr int kScanItems = 8;  // descriptors per thread per block of the scan
+constexpr int kScanItems = kMaxRanges / kCtaThreads;  // ranges per thread
 
-// One CTA.  res[t] = (carry entering tile t) << 63 | tokens emitted by tiles 0..t-1.
-__global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a, long long n_tiles) {
+// One CTA.  tile_status[w] = (carry entering warp w's range) << 63 | tokens emitted by ranges 0..w-1.
+__global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a, int n_ranges) {
     if (a.dense_flag != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.dense_flag) == 0u) {
         // the dense pass in front of this launch already produced the whole output: publish its totals
         const unsigned long long tokens = (a.n + 1) / 2;
@@ -223,68 +227,61 @@ __global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a,
         return;
     }
     __shared__ ScanFn warp_agg[32];
-    __shared__ uint32_t blk_carry_s;
-    __shared__ unsigned long long blk_base_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t *desc = a.scratch.tile_desc;
-    uint64_t *res = a.scratch.tile_status;
-    uint32_t blk_carry = 0;             // concrete carry / base at the start of the current block
-    unsigned long long blk_base = 0;
-    for (long long blk = 0; blk < n_tiles; blk += (long long)kCtaThreads * kScanItems) {
-        const long long t0 = blk + (long long)threadIdx.x * kScanItems;
-        uint32_t d[kScanItems];
+    const int t0 = threadIdx.x * kScanItems;
+    ScanFn item[kScanItems];
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) d[i] = (t0 + i < n_tiles) ? desc[t0 + i] : D_ID;  // identity padding
-        ScanFn agg = scan_decode(d[0]);
+    for (int i = 0; i < kScanItems; ++i) {
+        item[i].id = 1; item[i].cst = 0; item[i].delta = 0; item[i].cnt0 = 0;  // identity padding
+        if (t0 + i < n_ranges) {
+            const uint32_t d = a.scratch.tile_desc[t0 + i];
+            item[i].id = d >> 31; item[i].cst = (d >> 30) & 1u; item[i].delta = (d >> 29) & 1u;
+            item[i].cnt0 = a.scratch.tile_status[kMaxRanges + t0 + i];
+        }
+    }
+    ScanFn agg = item[0];
 #pragma unroll
-        for (int i = 1; i < kScanItems; ++i) agg = scan_compose(agg, scan_decode(d[i]));
-        // inclusive scan of the thread aggregates inside the warp, then across the 32 warps
-        ScanFn inc = agg;
+    for (int i = 1; i < kScanItems; ++i) agg = scan_compose(agg, item[i]);
+    ScanFn inc = agg;  // inclusive scan of the thread aggregates inside the warp, then across the 32 warps
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const ScanFn o = scan_shfl_up(inc, s);
+        if (lane >= s) inc = scan_compose(o, inc);
+    }
+    if (lane == 31) warp_agg[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        ScanFn wa = warp_agg[lane];
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
-            const ScanFn o = scan_shfl_up(inc, s);
-            if (lane >= s) inc = scan_compose(o, inc);
+            const ScanFn o = scan_shfl_up(wa, s);
+            if (lane >= s) wa = scan_compose(o, wa);
         }
-        if (lane == 31) warp_agg[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            ScanFn wa = warp_agg[lane];
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const ScanFn o = scan_shfl_up(wa, s);
-                if (lane >= s) wa = scan_compose(o, wa);
-            }
-            warp_agg[lane] = wa;  // inclusive over warps
-        }
-        __syncthreads();
-        // exclusive prefix function of this thread = (warps before) o (lanes before)
-        ScanFn ex;
-        ex.id = 1; ex.cst = 0; ex.delta = 0; ex.cnt0 = 0;
-        if (wid > 0) ex = warp_agg[wid - 1];
-        {
-            const ScanFn up = scan_shfl_up(inc, 1);
-            if (lane > 0) ex = scan_compose(ex, up);
-        }
-        uint32_t c = ex.id ? blk_carry : ex.cst;
-        unsigned long long b = blk_base + ex.cnt0 - ((blk_carry && ex.delta) ? 1u : 0u);
-#pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            if (t0 + i < n_tiles) {
-                res[t0 + i] = (c ? R_CARRY : 0ull) | b;
-                b += (d[i] & D_CNT) - ((c && (d[i] & D_DELTA)) ? 1u : 0u);
-                c = (d[i] & D_ID) ? c : ((d[i] >> 30) & 1u);
-            }
-        }
-        if (threadIdx.x == kCtaThreads - 1) { blk_carry_s = c; blk_base_s = b; }
-        __syncthreads();
-        blk_carry = blk_carry_s;
-        blk_base = blk_base_s;
-        __syncthreads();
+        warp_agg[lane] = wa;  // inclusive over warps
     }
-    if (threadIdx.x == 0) {
-        *a.scratch.total_tokens = blk_base;
-        *a.scratch.merged_any = (blk_base < a.n) ? 1u : 0u;
-        if (a.out_base_tokens + blk_base > a.out_cap_tokens) *a.scratch.overflow = 1u;
+    __syncthreads();
+    ScanFn ex;  // exclusive prefix function of this thread = (warps before) o (lanes before)
+    ex.id = 1; ex.cst = 0; ex.delta = 0; ex.cnt0 = 0;
+    if (wid > 0) ex = warp_agg[wid - 1];
+    {
+        const ScanFn up = scan_shfl_up(inc, 1);
+        if (lane > 0) ex = scan_compose(ex, up);
+    }
+    // the launch starts with carry 0 and nothing emitted
+    uint32_t c = ex.id ? 0u : ex.cst;
+    unsigned long long b = ex.cnt0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (t0 + i < n_ranges) {
+            a.scratch.tile_status[t0 + i] = (c ? R_CARRY : 0ull) | b;
+            b += item[i].cnt0 - ((c && item[i].delta) ? 1u : 0u);
+            c = item[i].id ? c : item[i].cst;
+        }
+    }
+    if (threadIdx.x == kCtaThreads - 1) {
+        *a.scratch.total_tokens = b;
+        *a.scratch.merged_any = (b < a.n) ? 1u : 0u;
+        if (a.out_base_tokens + b > a.out_cap_tokens) *a.scratch.overflow = 1u;
     }
 }
 
@@ -302,44 +299,96 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
     __syncthreads();
     const int lane = threadIdx.x & 31;
     uint16_t *stage = reinterpret_cast<uint16_t *>(smem + FE::TABLE_BYTES) + size_t(threadIdx.x >> 5) * C::STAGE_TOKENS;
-    const uint64_t *res = a.scratch.tile_status;
+    const long long warp = (long long)blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5);
     TileWalk<C::TILE_ELEMS> tw;
-    tw.init(a, (long long)blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5), (long long)gridDim.x * (kCtaThreads / 32));
-    for (; tw.tile < tw.n_tiles; tw.next(a)) {
+    tw.init(a, warp, (long long)gridDim.x * (kCtaThreads / 32));
+    if (tw.tile >= tw.end || warp >= kMaxRanges) return;
+    const uint64_t rv = a.scratch.tile_status[warp];
+    uint32_t carry = uint32_t(rv >> 63);
+    unsigned long long rel = rv & ~R_CARRY;                  // tokens emitted before the next round (this launch)
+    // Output streaming state.  stage[0 .. pend) holds tokens not yet written; stage[0] corresponds to
+    // a.out[wpos] and wpos is a multiple of 8 tokens (16 bytes).  The first `head` slots of the very first
+    // vector belong to the previous warp's range and must not be written.
+    unsigned long long wpos = (rel + a.out_base_tokens) & ~7ull;
+    uint32_t pend = uint32_t((rel + a.out_base_tokens) & 7ull);
+    uint32_t head = pend;
+    bool try_dense = true;  // attempt the half-lookup fast path; switched off after a miss, re-armed by a dense-looking round
+    // `total` new tokens were appended behind the pending ones: write out the whole 16-byte vectors and keep
+    // the < 8 leftover tokens at the front of the staging line for the next round
+    auto flush = [&](uint32_t total) {
+        const uint32_t have = pend + total;
+        const uint32_t nv = have >> 3;
+        const bool fits = (wpos + have <= a.out_cap_tokens);
+        if (!fits && lane == 0) *a.scratch.overflow = 1u;
+        if (fits) {
+            for (uint32_t v = lane; v < nv; v += 32) {
+                if (v == 0 && head != 0) {
+                    for (uint32_t k = head; k < 8; ++k) a.out[wpos + k] = stage[k];
+                } else {
+                    stg_stream_v4(a.out + wpos + 8 * v, *reinterpret_cast<const uint4 *>(stage + 8 * v));
+                }
+            }
+        }
+        const uint32_t rem = have & 7u;
+        uint16_t keep = 0;
+        if (nv != 0 && lane < rem) keep = stage[8 * nv + lane];
+        __syncwarp();
+        if (nv != 0) {
+            if (lane < rem) stage[lane] = keep;
+            head = 0;
+            wpos += 8ull * nv;
+            pend = rem;
+        } else {
+            pend = have;
+        }
+        __syncwarp();
+    };
+    for (; tw.tile < tw.end; tw.next(a)) {
         const unsigned long long tile_base = (unsigned long long)tw.tile * C::TILE_ELEMS;
         const bool simple = (tile_base + C::TILE_ELEMS < a.n) && (a.chunk == 0 || tw.ti.rem0 + C::TILE_ELEMS <= a.chunk);
         const bool end_wall = (a.chunk != 0) && (tw.ti.rem0 + C::TILE_ELEMS == a.chunk);
         uint4 w[R];
         uint32_t nx[R];
         load_tile3<FE, R>(a, tile_base, lane, w, nx);
-        const uint64_t rv = res[tw.tile];
-        uint32_t carry = uint32_t(rv >> 63);
-        unsigned long long rel = rv & ~R_CARRY;  // tokens emitted before this tile (this launch)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const uint32_t off = uint32_t(r * C::ROUND_ELEMS + lane * SEG);
             const unsigned long long g = tile_base + off;
             uint32_t next = __shfl_down_sync(FULL, FE::first_elem(w[r]), 1);
             if (lane == 31) next = nx[r];
-            const unsigned long long out_pos = rel + a.out_base_tokens;
             const bool wall_here = end_wall && r == R - 1 && lane == 31;
             // ---- dense warp-round: the pairs of the carry's parity are all rules ----
-            if (FE::kMembershipInValue && simple && (out_pos % (SEG / 2) == 0)) {
+            if (FE::kMembershipInValue && simple && try_dense) {
                 uint32_t hv[HV];
                 fe.lookup_vals(w[r], next, carry, hv);
                 const bool ok = FE::all_present(hv) && !(wall_here && carry);
                 if (__all_sync(FULL, ok)) {
-                    if (out_pos + C::ROUND_ELEMS / 2 <= a.out_cap_tokens) {
-                        uint16_t *dst = a.out + out_pos + size_t(lane) * (SEG / 2);
-                        if (SEG == 16) stg_stream_v4(dst, make_uint4(hv[0], hv[1], hv[HV > 2 ? 2 : 0], hv[HV > 3 ? 3 : 0]));
-                        else *reinterpret_cast<uint2 *>(dst) = make_uint2(hv[0], hv[1]);
-                    } else if (lane == 0) {
-                        *a.scratch.overflow = 1u;
+                    if (pend == 0) {  // output is vector-aligned: straight from registers
+                        if (wpos + C::ROUND_ELEMS / 2 <= a.out_cap_tokens) {
+                            uint16_t *dst = a.out + wpos + size_t(lane) * (SEG / 2);
+                            if (SEG == 16) stg_stream_v4(dst, make_uint4(hv[0], hv[1], hv[HV > 2 ? 2 : 0], hv[HV > 3 ? 3 : 0]));
+                            else *reinterpret_cast<uint2 *>(dst) = make_uint2(hv[0], hv[1]);
+                        } else if (lane == 0) {
+                            *a.scratch.overflow = 1u;
+                        }
+                        wpos += C::ROUND_ELEMS / 2;
+                    } else {          // an earlier break shifted the output: go through the staging line
+                        uint16_t *d = stage + pend + lane * (SEG / 2);
+                        if ((pend & 1u) == 0) {
+#pragma unroll
+                            for (int k = 0; k < HV; ++k) reinterpret_cast<uint32_t *>(d)[k] = hv[k];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < HV; ++k) { d[2 * k] = uint16_t(hv[k]); d[2 * k + 1] = uint16_t(hv[k] >> 16); }
+                        }
+                        __syncwarp();
+                        flush(uint32_t(C::ROUND_ELEMS / 2));
                     }
                     rel += C::ROUND_ELEMS / 2;
                     if (wall_here && a.chunk_ends != nullptr) a.chunk_ends[tw.ti.ck0] = a.chunk_ends_base + 2ull * rel;
                     continue;  // carry is unchanged
                 }
+                try_dense = false;
             }
             // ---- general warp-round ----
             uint32_t hv[HV], ov[HV], valid;
@@ -370,8 +419,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
                     a.chunk_ends[ck++] = a.chunk_ends_base + 2ull * (rel + pos + __popc(em & ((2u << d) - 1)));
                 }
             }
-            const uint32_t phase = uint32_t(out_pos & 7);  // keep the 16-byte phase of the output
-            uint32_t sp = phase + pos;
+            uint32_t sp = pend + pos;
 #pragma unroll
             for (int j = 0; j < SEG; ++j) {
                 if ((em >> j) & 1u) {
@@ -380,31 +428,23 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
                 }
             }
             __syncwarp();
-            if (out_pos + total <= a.out_cap_tokens) {
-                uint16_t *dst = a.out + (out_pos - phase);  // 16-byte aligned
-                const uint32_t lo = phase, hi = phase + total;
-                for (uint32_t v = lane; v * 8 < hi; v += 32) {
-                    const uint32_t t0 = v * 8;
-                    if (t0 >= lo && t0 + 8 <= hi) {
-                        stg_stream_v4(dst + t0, *reinterpret_cast<const uint4 *>(stage + t0));
-                    } else {
-                        for (uint32_t k = (t0 > lo ? t0 : lo); k < t0 + 8 && k < hi; ++k) dst[k] = stage[k];
-                    }
-                }
-            } else if (lane == 0) {
-                *a.scratch.overflow = 1u;
-            }
-            __syncwarp();
+            flush(total);
             rel += total;
             if (nid) carry = (cob >> (31 - __clz(nid))) & 1u;
+            // a round that merged (nearly) everything suggests dense input again
+            try_dense = (total <= uint32_t(C::ROUND_ELEMS / 2 + 2));
         }
+    }
+    // tail of the range: the leftover tokens (the next warp's range starts right behind them)
+    if (pend > head && lane >= head && lane < pend) {
+        if (wpos + pend <= a.out_cap_tokens) a.out[wpos + lane] = stage[lane];
+        else *a.scratch.overflow = 1u;
     }
 }
 
 template <class FE, int R>
 cudaError_t launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, cudaStream_t stream) {
     using C = Sweep3Cfg<FE, R>;
-    static_assert(size_t(C::TILE_ELEMS) >= kMinTileElems, "descriptor arrays are sized by kMinTileElems");
     constexpr size_t smem_count = FE::TABLE_BYTES;
     constexpr size_t smem_emit = FE::TABLE_BYTES + size_t(kCtaThreads / 32) * C::STAGE_TOKENS * 2;
     static_assert(smem_emit <= 227 * 1024, "shared memory budget");
@@ -422,17 +462,18 @@ cudaError_t launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, cud
         if (err != cudaSuccess) return err;
         configured[dev].store(true, std::memory_order_release);
     }
-    const size_t n_tiles = (a.n + C::TILE_ELEMS - 1) / C::TILE_ELEMS;
-    if (n_tiles + 1 > a.scratch.max_tiles) return cudaErrorInvalidValue;
+    if (a.scratch.max_tiles < size_t(2 * kMaxRanges)) return cudaErrorInvalidValue;
     // (the dense-abort word at ctrl+384 belongs to the dense pass enqueued in front of this launch: keep it)
     err = cudaMemsetAsync(a.scratch.ctrl, 0, 384, stream);
     if (err != cudaSuccess) return err;
+    const size_t n_tiles = (a.n + C::TILE_ELEMS - 1) / C::TILE_ELEMS;
     const size_t warps_per_cta = kCtaThreads / 32;
     size_t grid = (n_tiles + warps_per_cta - 1) / warps_per_cta;
     if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
+    if (grid > size_t(kMaxRanges) / warps_per_cta) grid = size_t(kMaxRanges) / warps_per_cta;
     if (grid == 0) grid = 1;
     kc<<<dim3(unsigned(grid)), dim3(kCtaThreads), smem_count, stream>>>(a, fp);
-    scan_kernel<<<1, kCtaThreads, 0, stream>>>(a, (long long)n_tiles);
+    scan_kernel<<<1, kCtaThreads, 0, stream>>>(a, int(grid * warps_per_cta));
     ke<<<dim3(unsigned(grid)), dim3(kCtaThreads), smem_emit, stream>>>(a, fp);
     return cudaGetLastError();
 }
