@@ -104,7 +104,7 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
             a.out_cap_tokens = out_cap / 2; a.out_base_tokens = 0;
             a.chunk_ends = d_chunk_ends; a.chunk_ends_base = 0;
             a.scratch = ws.scratch;
-            CUDA_TRY(bltk::launch_bpe_sweep_pairs(a, s->d_table, s->variant, stream));
+            CUDA_TRY(bltk::launch_bpe_sweep_pairs(a, s->d_table, s->variant, s->try_dense, stream));
             res->kind = DeviceResult::IN_SCRATCH;
             res->sweeps = 1;  // byte keys, ids >= 256: the reference's 2nd sweep cannot merge
             res->launches = 1;
@@ -229,7 +229,9 @@ static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **ou
         CUDA_TRY(cudaMemcpy(s->d_can_left, cl.data(), 8192, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(s->d_can_right, cr.data(), 8192, cudaMemcpyHostToDevice));
     }
+    // tuning / test switches: tile size of the exact sweep, and whether the dense pass runs in front of it
     if (const char *v = getenv("BLT_SWEEP_VARIANT")) s->variant = atoi(v);
+    if (const char *v = getenv("BLT_DENSE")) s->try_dense = (atoi(v) != 0);
     *out = s.release();
     return BLT_OK;
 }
@@ -246,13 +248,6 @@ blt_strategy::~blt_strategy() {
 }
 
 using namespace bltc;
-
-#ifdef BLT_TRACE
-namespace bltk { cudaError_t debug_set_trace(unsigned long long *d_buf, unsigned int iters); }
-extern "C" __attribute__((visibility("default"))) int blt_debug_set_trace(void *d_buf, unsigned int iters) {
-    return bltk::debug_set_trace(static_cast<unsigned long long *>(d_buf), iters) == cudaSuccess ? 0 : -5;
-}
-#endif
 
 extern "C" {
 

@@ -1,10 +1,11 @@
 // kernels.cuh -- launch interface of the sm_100a kernels behind libblt_cuda.so.
 //
 // K1  widen_kernel        BasicTokenizationStrategy::process_chunk  (blt_core/src/tokenizer.rs:108-123)
-// K2  bpe_sweep_kernel    one sweep of BpeStrategy::process_chunk   (blt_core/src/tokenizer.rs:63-86)
-//                         in its closed parallel form: pair lookup -> run parity ->
-//                         single-pass decoupled look-back -> compaction -> big-endian u16 store.
-// K3  the same sweep over u16 tokens with a general HashMap<(u16,u16),u16> (lib.rs:75).
+// K2  dense_pairs_kernel  one sweep of BpeStrategy::process_chunk   (blt_core/src/tokenizer.rs:63-86)
+//     + count/scan/emit   in its closed parallel form: a speculative streaming pass for
+//                         merge-dense input, and the exact three-launch sweep (pair lookup -> run parity ->
+//                         per-range carry functions -> scan -> compaction -> big-endian u16 store).
+// K3  the same exact sweep over u16 tokens with a general HashMap<(u16,u16),u16> (lib.rs:75).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -42,17 +43,15 @@ struct HashTableView {
     const uint32_t *can_right; // device bitmap, 65 536 bits: token appears as a right component
 };
 
-// Per-launch scratch in device memory (zeroed by the launcher before every sweep).
+// Per-launch scratch in device memory (the control block is zeroed by the launcher before every sweep).
 struct SweepScratch {
     void *ctrl;              // start of the region: 512-byte control block, then the descriptors
     uint64_t *total_tokens;  // ctrl+0  : number of tokens written by the sweep
     uint32_t *merged_any;    // ctrl+12 : set to 1 if any pair merged in this sweep
     uint32_t *overflow;      // ctrl+16 : set to 1 if the output capacity was exceeded
-    uint32_t *tile_counter;  // ctrl+128: dynamic tile id dispenser (own 128-byte line)
-    uint32_t *phase_hint;    // ctrl+256: (unused since tiles are assigned statically)
     uint32_t *dense_abort;   // ctrl+384: set by the dense kernel when its speculation fails (own line)
-    uint64_t *tile_status;   // ctrl+512: one word per tile (look-back descriptors / scan results)
-    uint32_t *tile_desc;     // after tile_status: one word per tile (carry function + token count)
+    uint64_t *tile_status;   // ctrl+512: per warp range: [w] carry_in<<63 | tokens before; [8192+w] tokens of the range
+    uint32_t *tile_desc;     // after tile_status: per warp range: carry function flags
     size_t bytes;            // size of the whole region
     size_t max_tiles;
 };
@@ -81,14 +80,14 @@ cudaError_t launch_widen(const uint8_t *d_in, size_t n, uint8_t *d_out, cudaStre
 cudaError_t launch_fill_chunk_ends(uint64_t *d_ends, size_t n, size_t chunk, unsigned bytes_per_elem,
                                    cudaStream_t stream);
 // K2.  d_table = kPairTableEntries u16 in device memory (layout above).
-cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, int variant,
+// try_dense: enqueue the speculative dense pass in front of the exact sweep.
+cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, int variant, bool try_dense,
                                    cudaStream_t stream);
 // K3.  in_is_u16: input is BE u16 tokens (true) or raw bytes (false).
 cudaError_t launch_bpe_sweep_hash(const SweepArgs &a, const HashTableView &t, bool in_is_u16,
                                   cudaStream_t stream);
-// Number of kernels the launchers above enqueue per call (for bench.py's gpu_launches claim):
-// one memset node + one kernel.
-constexpr int kLaunchesPerSweep = 1;
+// Kernels enqueued per K2 call: dense_pairs_kernel + count + scan + emit (bench.py's gpu_launches claim).
+constexpr int kLaunchesPerSweep = 4;
 
 int num_sweep_variants();
 const char *sweep_variant_name(int variant);

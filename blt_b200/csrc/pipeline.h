@@ -87,7 +87,8 @@ struct blt_strategy {
     bltk::HashSlot *d_slots = nullptr;    // K3 hash table
     uint32_t *d_can_left = nullptr, *d_can_right = nullptr;
     uint32_t hash_mask = 0;
-    int variant = 0;                      // K2 tile configuration
+    int variant = 0;                      // K2 tile configuration of the exact sweep
+    bool try_dense = true;                // K2: run the speculative dense pass first
     std::mutex resident_mu;
     bltc::Workspace resident;             // workspace of blt_process_resident
     bltc::DeviceResult resident_result;

@@ -119,9 +119,11 @@ def _random_case(rng, n, alphabet, density):
     return np.ascontiguousarray(data), pairs
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
-def test_random_vs_oracle_all_variants(nat, torch_mod, oracle, variant, monkeypatch):
+@pytest.mark.parametrize("variant,dense", [(0, True), (1, True), (0, False), (1, False)])
+def test_random_vs_oracle_all_variants(nat, torch_mod, oracle, variant, dense, monkeypatch):
+    """Both tile sizes of the exact sweep, with and without the dense speculative pass in front."""
     monkeypatch.setenv("BLT_SWEEP_VARIANT", str(variant))
+    monkeypatch.setenv("BLT_DENSE", "1" if dense else "0")
     c = nat.Context(0)
     rng = random.Random(1000 + variant)
     sizes = [1, 2, 15, 16, 17, 255, 4095, 4096, 4097, 8191, 8193, 16384, 65537, 300001, 1 * MiB + 3, 5 * MiB + 11]

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 
 from blt_b200 import _native as nat, synth  # noqa: E402
 
-VARIANT_NAMES = ["sweep3 R=4", "sweep3 R=8", "v2", "v3", "v4", "v5"]
+VARIANT_NAMES = ["exact r4", "exact r8"]
 
 
 def time_resident(strat, d_in, n, chunk, d_out, iters):
@@ -38,7 +38,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bytes", type=int, default=1 << 30)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--variants", default="0,1,2,3,4,5")
+    ap.add_argument("--variants", default="0")
     ap.add_argument("--configs", default="1,2,3,4")
     args = ap.parse_args()
     n, chunk = args.bytes, 16 << 20
@@ -70,6 +70,8 @@ def main():
                 l, r = synth.merges_from_sample(data, 256 if cfg == 2 else 32768)
                 strat = ctx.bpe_from_pairs({(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))})
                 name = VARIANT_NAMES[v]
+            if cfg != 1:
+                name = ("dense+" if os.environ.get("BLT_DENSE", "1") != "0" else "") + name
             out_len, med, best = time_resident(strat, d_in, n, chunk, d_out, args.iters)
             alg = n + out_len
             print(json.dumps({"config": cfg, "kernel": name, "n": n, "out_bytes": out_len, "ratio_tokens_per_byte": round(out_len / 2 / n, 4),
