@@ -25,7 +25,8 @@ namespace {
 constexpr int kCtaThreads = 1024;
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int kMaxDevices = 64;
-constexpr size_t kCtrlBytes = 512;  // results | (spare) | (spare) | the dense pass's abort word, 128 bytes each
+constexpr size_t kCtrlBytes = 512;  // results | (spare) | the dense pass's work counter | its abort word, 128 bytes each
+constexpr uint32_t kDenseUnitSegs = 512;  // 8 KiB of input per warp and work unit
 
 int sm_count(int dev) {
     static std::atomic<int> cached[kMaxDevices];
@@ -171,11 +172,14 @@ struct PairsFE {
         const uint32_t t = ((vals[0] & c) + c) & ((vals[1] & c) + c) & ((vals[2] & c) + c) & ((vals[3] & c) + c);
         return (t & 0x01000100u) == 0x01000100u;
     }
+    // bit i <-> token i present.  The low bytes of four tokens are gathered into one word (PRMT), a SWAR
+    // "byte != 0" sets bit 7 of each byte, and one multiply collects those four bits.
+    __device__ __forceinline__ static uint32_t nonzero_bytes4(uint32_t x) {
+        const uint32_t y = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
+        return (((y >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+    }
     __device__ __forceinline__ static uint32_t present_mask(const uint32_t *vals) {
-        uint32_t m = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m |= (((vals[i >> 1] >> (16 * (i & 1))) & 0xffu) ? 1u : 0u) << i;
-        return m;
+        return nonzero_bytes4(__byte_perm(vals[0], vals[1], 0x6420)) | (nonzero_bytes4(__byte_perm(vals[2], vals[3], 0x6420)) << 4);
     }
     __device__ __forceinline__ uint32_t lookup_half(const uint4 &w, uint32_t next, uint32_t par, uint32_t *vals) const {
         lookup_vals(w, next, par, vals);
@@ -270,23 +274,42 @@ struct HashFE {
 // ================================================================================================
 __global__ void __launch_bounds__(kCtaThreads, 1)
 dense_pairs_kernel(const unsigned char *__restrict__ in, unsigned long long n, uint16_t *__restrict__ out,
-                   const uint16_t *__restrict__ table, uint32_t *abort_flag) {
+                   const uint16_t *__restrict__ table, uint32_t *abort_flag, uint32_t *work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     PairsFE fe;
     PairsFE::Params p{table};
     fe.init(p, smem);
     __syncthreads();
+    // Work is handed out per warp in units of kDenseUnitSegs consecutive 16-byte segments: the first unit
+    // of a warp is static, the following ones come from one global counter (an SM that gets less memory
+    // bandwidth than its neighbours simply takes fewer units; with a static split the slowest SM set the
+    // kernel time).  A unit is TRIPS trips of U independent 16-byte loads per lane; the loads of the next
+    // trip - and the counter fetch of the next unit - are issued before the current trip is looked up and
+    // stored, so a warp always has U..2U loads in flight and never waits for the counter.
+    constexpr int U = 4;
+    constexpr uint32_t TRIPS = kDenseUnitSegs / (U * 32);
     const unsigned long long n_segs = n / 16;
-    const unsigned long long stride = (unsigned long long)gridDim.x * kCtaThreads;
-    unsigned long long seg = (unsigned long long)blockIdx.x * kCtaThreads + threadIdx.x;
+    const uint32_t full_units = uint32_t(n_segs / kDenseUnitSegs);
     const int lane = threadIdx.x & 31;
+    const uint32_t n_static = gridDim.x * (kCtaThreads / 32);
     bool bad = false;
-    uint32_t ab = 0;  // the abort word as it was one trip ago: never waited for inside a trip
-    constexpr int U = 4;  // independent 16-byte loads in flight per thread
-    for (; seg + (U - 1) * stride < n_segs; seg += U * stride) {
-        uint4 w[U];
+    uint32_t ab = 0;       // the abort word as it was one trip ago: never waited for inside a trip
+    uint32_t nxt_raw = 0;  // lane 0: the unit after the current one (fetched one unit ahead)
+    if (lane == 0) nxt_raw = atomicAdd(work_counter, 1u) + n_static;
+    struct Pos { uint32_t unit, t; };
+    auto advance = [&](Pos q) -> Pos {
+        if (q.t + 1 < TRIPS) return Pos{q.unit, q.t + 1};
+        const uint32_t u = __shfl_sync(FULL, nxt_raw, 0);
+        if (lane == 0 && u < full_units) nxt_raw = atomicAdd(work_counter, 1u) + n_static;
+        return Pos{u, 0};
+    };
+    auto seg_of = [&](Pos q) { return (unsigned long long)q.unit * kDenseUnitSegs + q.t * (U * 32) + lane; };
+    auto load = [&](uint4 *w, unsigned long long s0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) w[u] = ldg_stream_v4(in + (seg + u * stride) * 16);
+        for (int u = 0; u < U; ++u) w[u] = ldg_stream_v4(in + (s0 + u * 32) * 16);
+    };
+    // looks up and stores one trip; true = this warp or somebody else gave up
+    auto work = [&](const uint4 *w, unsigned long long s0) {
         const uint32_t ab_now = ab;
         if (lane == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(abort_flag) : "memory");
 #pragma unroll
@@ -294,12 +317,28 @@ dense_pairs_kernel(const unsigned char *__restrict__ in, unsigned long long n, u
             uint32_t v[4];
             fe.lookup_vals(w[u], 0u, 0u, v);
             bad = bad || !PairsFE::all_present(v);
-            stg_stream_v4(out + (seg + u * stride) * 8, make_uint4(v[0], v[1], v[2], v[3]));
+            stg_stream_v4(out + (s0 + u * 32) * 8, make_uint4(v[0], v[1], v[2], v[3]));
         }
-        if (__any_sync(FULL, bad || ab_now != 0)) break;  // this warp or somebody else gave up: stop streaming
+        return __any_sync(FULL, bad || ab_now != 0) != 0;
+    };
+    uint4 wa[U], wb[U];
+    Pos pa{blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5), 0}, pb{0, 0};
+    bool more = pa.unit < full_units;
+    if (more) load(wa, seg_of(pa));
+    while (more) {
+        pb = advance(pa);
+        const bool next = pb.unit < full_units;
+        if (next) load(wb, seg_of(pb));
+        if (work(wa, seg_of(pa)) || !next) break;
+        pa = advance(pb);
+        more = pa.unit < full_units;
+        if (more) load(wa, seg_of(pa));
+        if (work(wb, seg_of(pb))) break;
     }
-    if (!__any_sync(FULL, bad || ab != 0)) {
-        for (; seg < n_segs; seg += stride) {
+    // the segments behind the last full unit (fewer than kDenseUnitSegs)
+    if (blockIdx.x == gridDim.x - 1 && !bad) {
+        for (unsigned long long seg = (unsigned long long)full_units * kDenseUnitSegs + threadIdx.x; seg < n_segs;
+             seg += kCtaThreads) {
             const uint4 w0 = ldg_stream_v4(in + seg * 16);
             uint32_t v[4];
             fe.lookup_vals(w0, 0u, 0u, v);
@@ -316,7 +355,8 @@ dense_pairs_kernel(const unsigned char *__restrict__ in, unsigned long long n, u
         }
         if (i < n) out[i / 2] = uint16_t(uint32_t(in[i]) << 8);  // odd length: the last element stays a raw token
     }
-    if (bad) *reinterpret_cast<volatile uint32_t *>(abort_flag) = 1u;
+    // one store per CTA: 150 000 threads storing to one word serialise in L2 for tens of microseconds
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(abort_flag) = 1u;
 }
 
 // ================================================================================================
@@ -439,14 +479,16 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a_in, const uint16_t *d_tabl
             configured[dev].store(true, std::memory_order_release);
         }
         // the exact launch below zeroes the control block too; the abort word must be clear before the dense pass
-        err = cudaMemsetAsync(a.scratch.dense_abort, 0, 4, stream);
+        // (one memset: work counter at +256, abort word at +384)
+        err = cudaMemsetAsync(static_cast<unsigned char *>(a.scratch.ctrl) + 256, 0, 132, stream);
         if (err != cudaSuccess) return err;
-        const size_t n_segs = a.n / 16;
-        size_t grid = (n_segs + kCtaThreads - 1) / kCtaThreads;
+        const size_t units = a.n / 16 / kDenseUnitSegs;
+        size_t grid = (units + kCtaThreads / 32 - 1) / (kCtaThreads / 32);
         if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
         if (grid == 0) grid = 1;
         dense_pairs_kernel<<<dim3(unsigned(grid)), dim3(kCtaThreads), PairsFE::TABLE_BYTES, stream>>>(
-            static_cast<const unsigned char *>(a.in), a.n, a.out + a.out_base_tokens, d_table, a.scratch.dense_abort);
+            static_cast<const unsigned char *>(a.in), a.n, a.out + a.out_base_tokens, d_table, a.scratch.dense_abort,
+            reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(a.scratch.ctrl) + 256));
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         a.dense_flag = a.scratch.dense_abort;

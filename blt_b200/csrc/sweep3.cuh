@@ -85,15 +85,29 @@ __device__ __forceinline__ void load_tile3(const SweepArgs &a, unsigned long lon
 
 // Membership word of one segment (both parities looked up), with walls and the end of input applied.
 // hv / ov receive the tokens of the even / odd positions (raw token at wall positions).
+// have_par >= 0: the tokens of that parity are already in hv (from a dense attempt) and are not looked up again.
 template <class FE, int TILE_ELEMS>
 __device__ __forceinline__ uint32_t segment_full(const FE &fe, const SweepArgs &a, const TileInfo &ti, bool simple,
                                                  bool end_wall_here, uint32_t off, unsigned long long g, const uint4 &w,
                                                  uint32_t next, uint32_t *hv, uint32_t *ov, uint32_t *valid_out,
-                                                 Walls<FE::SEG> *wl_out) {
+                                                 Walls<FE::SEG> *wl_out, int have_par = -1) {
     constexpr int SEG = FE::SEG;
     constexpr uint32_t ALL = (1u << SEG) - 1;
-    const uint32_t hp = fe.lookup_half(w, next, 0u, hv);
-    const uint32_t op = fe.lookup_half(w, next, 1u, ov);
+    uint32_t hp, op;
+    if (FE::kMembershipInValue && have_par >= 0) {
+        if (have_par == 1) {  // hv holds the odd positions: move them over and look the even ones up
+#pragma unroll
+            for (int k = 0; k < SEG / 4; ++k) ov[k] = hv[k];
+            fe.lookup_vals(w, next, 0u, hv);
+        } else {
+            fe.lookup_vals(w, next, 1u, ov);
+        }
+        hp = FE::present_mask(hv);
+        op = FE::present_mask(ov);
+    } else {
+        hp = fe.lookup_half(w, next, 0u, hv);
+        op = fe.lookup_half(w, next, 1u, ov);
+    }
     Walls<SEG> wl;
     wl.endm = 0;
     wl.ck = ti.ck0;
@@ -312,7 +326,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
     unsigned long long wpos = (rel + a.out_base_tokens) & ~7ull;
     uint32_t pend = uint32_t((rel + a.out_base_tokens) & 7ull);
     uint32_t head = pend;
-    bool try_dense = true;  // attempt the half-lookup fast path; switched off after a miss, re-armed by a dense-looking round
     // `total` new tokens were appended behind the pending ones: write out the whole 16-byte vectors and keep
     // the < 8 leftover tokens at the front of the staging line for the next round
     auto flush = [&](uint32_t total) {
@@ -358,9 +371,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
             if (lane == 31) next = nx[r];
             const bool wall_here = end_wall && r == R - 1 && lane == 31;
             // ---- dense warp-round: the pairs of the carry's parity are all rules ----
-            if (FE::kMembershipInValue && simple && try_dense) {
-                uint32_t hv[HV];
+            uint32_t hv[HV], ov[HV], valid;
+            int have_par = -1;
+            if (FE::kMembershipInValue && simple) {
                 fe.lookup_vals(w[r], next, carry, hv);
+                have_par = int(carry);
                 const bool ok = FE::all_present(hv) && !(wall_here && carry);
                 if (__all_sync(FULL, ok)) {
                     if (pend == 0) {  // output is vector-aligned: straight from registers
@@ -388,12 +403,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
                     if (wall_here && a.chunk_ends != nullptr) a.chunk_ends[tw.ti.ck0] = a.chunk_ends_base + 2ull * rel;
                     continue;  // carry is unchanged
                 }
-                try_dense = false;
             }
-            // ---- general warp-round ----
-            uint32_t hv[HV], ov[HV], valid;
+            // ---- general warp-round: the other parity too (the first one is reused), full membership word ----
             Walls<SEG> wl;
-            const uint32_t m = segment_full<FE, C::TILE_ELEMS>(fe, a, tw.ti, simple, wall_here, off, g, w[r], next, hv, ov, &valid, &wl);
+            const uint32_t m = segment_full<FE, C::TILE_ELEMS>(fe, a, tw.ti, simple, wall_here, off, g, w[r], next, hv, ov, &valid, &wl,
+                                                               have_par);
             const uint32_t lead = __clz(~(m << (32 - SEG)));
             const uint32_t nid = ~__ballot_sync(FULL, m == ALL);
             const uint32_t cob = __ballot_sync(FULL, (lead & 1u) != 0);
@@ -419,20 +433,26 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
                     a.chunk_ends[ck++] = a.chunk_ends_base + 2ull * (rel + pos + __popc(em & ((2u << d) - 1)));
                 }
             }
-            uint32_t sp = pend + pos;
+            // one predicated 2-byte shared store + one predicated pointer bump per position
+            uint32_t sp = uint32_t(__cvta_generic_to_shared(stage + pend + pos));
 #pragma unroll
             for (int j = 0; j < SEG; ++j) {
-                if ((em >> j) & 1u) {
-                    const uint32_t v = (j & 1) ? ov[j >> 2] : hv[j >> 2];
-                    stage[sp++] = uint16_t(((j >> 1) & 1) ? (v >> 16) : v);
-                }
+                const uint32_t v = (j & 1) ? ov[j >> 2] : hv[j >> 2];
+                const uint32_t tok = ((j >> 1) & 1) ? (v >> 16) : v;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .b16 t;\n\t"
+                    "setp.ne.u32 p, %2, 0;\n\t"
+                    "cvt.u16.u32 t, %1;\n\t"
+                    "@p st.shared.u16 [%0], t;\n\t"
+                    "@p add.u32 %0, %0, 2;\n\t}"
+                    : "+r"(sp)
+                    : "r"(tok), "r"(em & (1u << j))
+                    : "memory");
             }
             __syncwarp();
             flush(total);
             rel += total;
             if (nid) carry = (cob >> (31 - __clz(nid))) & 1u;
-            // a round that merged (nearly) everything suggests dense input again
-            try_dense = (total <= uint32_t(C::ROUND_ELEMS / 2 + 2));
         }
     }
     // tail of the range: the leftover tokens (the next warp's range starts right behind them)
