@@ -357,6 +357,61 @@ struct OffsetBoard {
     }
 };
 
+// Fresh tmpfs / page-cache pages are the slowest part of writing the output: eight threads storing into a
+// newly truncated shared mapping fault pages in at ~8 GB/s together, whereas fallocate() produces them at
+// ~14 GB/s from ONE thread and stores into pages that exist run at 20-90 GB/s (tools/tmpfs_probe.cpp, numbers
+// in DESIGN.md).  This thread walks ahead of the writers - it starts before the CUDA context is created, so
+// the first gigabytes are ready by the time the first chunk comes back - allocating the pages and mapping
+// them.  Purely an accelerator: if fallocate is not supported the writers fault pages in as before.
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+class OutPrealloc {
+  public:
+    ~OutPrealloc() { finish(); }
+    void start(int fd, uint8_t *map, uint64_t bound, uint64_t sure) {
+        fd_ = fd; map_ = map; bound_ = bound;
+        want_.store(std::min(sure, bound));
+        th_ = std::thread([this] { loop(); });
+    }
+    // the writers have reached `written`; keep `ahead` more bytes ready
+    void advance(uint64_t written, uint64_t ahead) {
+        uint64_t lo = low_.load(std::memory_order_relaxed);
+        while (lo < written && !low_.compare_exchange_weak(lo, written, std::memory_order_relaxed)) {}
+        const uint64_t w = std::min(bound_, written + ahead);
+        uint64_t cur = want_.load(std::memory_order_relaxed);
+        while (cur < w && !want_.compare_exchange_weak(cur, w, std::memory_order_relaxed)) {}
+    }
+    void finish() {
+        stop_.store(true);
+        if (th_.joinable()) th_.join();
+    }
+    uint64_t prepared() const { return done_.load(std::memory_order_relaxed); }
+
+  private:
+    void loop() {
+        constexpr uint64_t kPiece = uint64_t(32) << 20;
+        uint64_t done = 0;
+        while (!stop_.load(std::memory_order_relaxed) && done < bound_) {
+            const uint64_t lo = low_.load(std::memory_order_relaxed) & ~(kPiece - 1);
+            if (done < lo) done = lo;  // the writers overtook us: do not redo what they faulted in themselves
+            const uint64_t w = want_.load(std::memory_order_relaxed);
+            if (done >= w) { std::this_thread::sleep_for(std::chrono::microseconds(200)); continue; }
+            const uint64_t len = std::min(kPiece, bound_ - done);
+            if (fallocate(fd_, 0, off_t(done), off_t(len)) != 0) return;
+            (void)madvise(map_ + done, size_t((len + 4095) & ~uint64_t(4095)), MADV_POPULATE_WRITE);  // best effort
+            done += len;
+            done_.store(done, std::memory_order_relaxed);
+        }
+    }
+    int fd_ = -1;
+    uint8_t *map_ = nullptr;
+    uint64_t bound_ = 0;
+    std::atomic<uint64_t> want_{0}, low_{0}, done_{0};
+    std::atomic<bool> stop_{false};
+    std::thread th_;
+};
+
 int build_like(blt_ctx *ctx, const blt_strategy *proto, blt_strategy **out) {
     switch (proto->mode) {
         case Mode::Basic: return blt_strategy_basic(ctx, out);
@@ -445,7 +500,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         of.fd = 1;
         of.seekable = false;
     }
-    auto cleanup = [&]() {
+    auto close_io = [&]() {
         if (map) munmap(const_cast<uint8_t *>(map), n);
         if (in_is_file) close(in_fd);
         if (cfg->output) close(of.fd);
@@ -456,7 +511,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         const uint16_t t = blt_content_type_token(cfg->content_type);
         const uint8_t be[2] = {uint8_t(t >> 8), uint8_t(t & 0xff)};
         int rc = of.write_at(be, 2, 0);
-        if (rc) { cleanup(); return rc; }
+        if (rc) { close_io(); return rc; }
         prefix = 2;
     }
 
@@ -479,9 +534,41 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
                 off += uint64_t(r);
             }
         }
-        cleanup();
+        close_io();
         return rc;
     }
+
+    // ---- the mmap path's output: mapped at its upper bound, pages prepared in the background from now on
+    // (the CUDA context creation below takes 0.4-1.5 s, which is when the first gigabytes get ready) ----
+    const size_t n_chunks = (in_is_file && n) ? (n + chunk - 1) / chunk : 0;
+    OutPrealloc pre;
+    if (n_chunks && of.seekable && getenv("BLT_NO_MMAP_OUT") == nullptr) {
+        struct stat ost;
+        const size_t bound = size_t(prefix) + 2 * n;
+        if (fstat(of.fd, &ost) == 0 && S_ISREG(ost.st_mode) && ftruncate(of.fd, off_t(bound)) == 0) {
+            // O_WRONLY descriptors cannot be mapped shared: reopen read-write through /proc
+            const std::string self = "/proc/self/fd/" + std::to_string(of.fd);
+            const int rw = open(self.c_str(), O_RDWR);
+            if (rw >= 0) {
+                void *m = mmap(nullptr, bound, PROT_READ | PROT_WRITE, MAP_SHARED, rw, 0);
+                close(rw);
+                if (m != MAP_FAILED) { of.map = static_cast<uint8_t *>(m); of.map_len = bound; }
+            }
+            if (!of.map) (void)!ftruncate(of.fd, off_t(prefix));
+        }
+        // every strategy but passthrough writes at least n bytes (BPE: >= n/2 tokens of 2 bytes; basic: 2n)
+        if (of.map && getenv("BLT_NO_PREALLOC") == nullptr)
+            pre.start(of.fd, of.map, bound, mode == Mode::Basic ? bound : prefix + n);
+    }
+    auto cleanup = [&]() {
+        pre.finish();
+        if (of.map) {  // an early error: give the mapping back and leave only what was written
+            munmap(of.map, of.map_len);
+            of.map = nullptr;
+            (void)!ftruncate(of.fd, off_t(prefix));
+        }
+        close_io();
+    };
 
     slog.mark("config parsed, io open");
     int n_dev = 0;
@@ -529,23 +616,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     }
 
     // ---- mmap path: run_mmap_pipeline (pipeline.rs:56-131) over n_gpus devices ----
-    const size_t n_chunks = n ? (n + chunk - 1) / chunk : 0;
     if (n_chunks == 0) { cleanup(); return BLT_OK; }  // empty file -> empty output (pipeline.rs:103-105)
-    if (of.seekable && getenv("BLT_NO_MMAP_OUT") == nullptr) {
-        struct stat ost;
-        const size_t bound = size_t(prefix) + 2 * n;
-        if (fstat(of.fd, &ost) == 0 && S_ISREG(ost.st_mode) && ftruncate(of.fd, off_t(bound)) == 0) {
-            // O_WRONLY descriptors cannot be mapped shared: reopen read-write through /proc
-            const std::string self = "/proc/self/fd/" + std::to_string(of.fd);
-            const int rw = open(self.c_str(), O_RDWR);
-            if (rw >= 0) {
-                void *m = mmap(nullptr, bound, PROT_READ | PROT_WRITE, MAP_SHARED, rw, 0);
-                close(rw);
-                if (m != MAP_FAILED) { of.map = static_cast<uint8_t *>(m); of.map_len = bound; }
-            }
-            if (!of.map) (void)!ftruncate(of.fd, off_t(prefix));
-        }
-    }
     if (size_t(n_gpus) > n_chunks) n_gpus = int(n_chunks);
     // Chunk k goes to GPU k % G: the pipelines advance through the file together, so a chunk's offset (the
     // lengths of all earlier chunks) is known almost as soon as its own bytes are back on the host.
@@ -556,6 +627,9 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     proto.mode = mode;
     proto.rules = rules;
 
+    std::mutex drain_mu;
+    std::condition_variable drain_cv;
+    int drained = 0;
     auto worker = [&](size_t g) {
         GpuShard &sh = shards[g];
         blt_ctx *ctx = nullptr;
@@ -586,6 +660,9 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
             return of.write_at(buf, len, off);
         };
         uint64_t produced = 0;
+        double t_in = 0, t_out = 0, t_wait = 0;  // host seconds: staging copies in, copies out, waiting for D2H
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(now() - a).count(); };
         if (rc == BLT_OK) {
             ChunkSource src;
             src.n = n; src.chunk = chunk; src.first = g; src.stride = size_t(n_gpus);
@@ -597,11 +674,16 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
             struct Pending { Slot *sl = nullptr; size_t len = 0, id = 0; } pend;
             auto flush = [&](Pending &p) -> int {
                 if (!p.sl) return BLT_OK;
+                auto t0 = now();
                 CUDA_TRY(cudaEventSynchronize(p.sl->ev_d2h));
                 // Basic is fixed-ratio: the offset is known up front; otherwise ask the board
                 const int64_t base = (mode == Mode::Basic) ? int64_t(2 * p.id * chunk) : board.base_of(p.id);
                 if (base < 0) return fail(BLT_ERR_IO, "another GPU pipeline failed");
+                t_wait += since(t0);
+                t0 = now();
                 const int w = put(p.sl->h_out, p.len, prefix + uint64_t(base));
+                t_out += since(t0);
+                pre.advance(prefix + uint64_t(base) + p.len, uint64_t(1) << 30);
                 produced += p.len;
                 p.sl = nullptr;
                 return w;
@@ -610,7 +692,9 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
                 rc = run_slots(
                     st, *pipe, src,
                     [&](size_t id, Slot &sl) {
+                        const auto t0 = now();
                         par_memcpy(sl.h_in, map + id * chunk, src.len_of(id));  // page cache -> pinned
+                        t_in += since(t0);
                         return static_cast<const uint8_t *>(sl.h_in);
                     },
                     [&](size_t id, Slot &sl, size_t len) -> int {
@@ -628,12 +712,20 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
             }
         }
         sh.total = produced;
-        slog.mark("pipeline drained", sh.device);
         if (rc != BLT_OK) { sh.rc = rc; sh.err = blt_last_error(); board.fail_all(); }
+        slog.mark("pipeline drained", sh.device);
+        if (slog.on)
+            std::fprintf(stderr, "[blt] gpu%d host seconds: copy-in %.3f, copy-out %.3f, waiting for the device %.3f (%zu threads)\n",
+                         sh.device, t_in, t_out, t_wait, io.width());
+        {   // from here on this thread only gives device resources back; the files are the main thread's
+            std::lock_guard<std::mutex> lk(drain_mu);
+            ++drained;
+        }
+        drain_cv.notify_all();
         if (pipe) { pipe->release(); }
         if (st) blt_strategy_destroy(st);
         if (ctx) blt_ctx_destroy(ctx);
-        slog.mark("released", sh.device);
+        slog.mark("device resources released", sh.device);
     };
 
     std::vector<std::thread> pool;
@@ -641,8 +733,14 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         shards[g].device = int(g);
         pool.emplace_back(worker, g);
     }
-    for (auto &t : pool) t.join();
-    slog.mark("all shards done");
+    {
+        std::unique_lock<std::mutex> lk(drain_mu);
+        drain_cv.wait(lk, [&] { return drained == n_gpus; });
+    }
+    // Every chunk is in the output mapping.  Unmapping gigabytes of populated pages takes 0.1-0.3 s, the same
+    // order as freeing the pinned buffers and the context, so the two teardowns run side by side.
+    pre.finish();
+    if (slog.on) std::fprintf(stderr, "[blt] output pages prepared ahead of the writers: %.2f GiB\n", double(pre.prepared()) / double(1 << 30));
     rc = BLT_OK;
     for (const auto &sh : shards)
         if (sh.rc != BLT_OK && rc == BLT_OK) { rc = sh.rc; fail(sh.rc, sh.err); }  // first error in chunk order
@@ -652,8 +750,12 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         munmap(of.map, of.map_len);
         of.map = nullptr;
         if (ftruncate(of.fd, off_t(total)) != 0 && rc == BLT_OK) rc = fail(BLT_ERR_IO, "ftruncate failed");
-        slog.mark("output trimmed");
+        slog.mark("output unmapped and trimmed");
     }
+    if (map) { munmap(const_cast<uint8_t *>(map), n); map = nullptr; }
+    slog.mark("input unmapped");
+    for (auto &t : pool) t.join();
+    slog.mark("all shards done");
     cleanup();
     return rc;
 }

@@ -44,9 +44,9 @@ for g in [int(x) for x in args.gpus.split(",")]:
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
         # in-process stage log: pipeline time = last "pipe buffers allocated" .. "output trimmed"/"all shards done"
-        marks = [(float(l.split("ms]")[0].split("[blt")[1]), l) for l in r.stderr.splitlines() if l.startswith("[blt")]
+        marks = [(float(l.split("ms]")[0].split("[blt")[1]), l) for l in r.stderr.splitlines() if l.startswith("[blt") and " ms]" in l]
         t_ready = max((t for t, l in marks if "pipe buffers allocated" in l), default=None)
-        t_done = max((t for t, l in marks if "output trimmed" in l or "all shards done" in l), default=None)
+        t_done = max((t for t, l in marks if "all shards done" in l), default=None)
         if t_ready is not None and t_done is not None:
             pipe_s = (t_done - t_ready) / 1e3
             best_pipe = pipe_s if best_pipe is None else min(best_pipe, pipe_s)
@@ -54,7 +54,7 @@ for g in [int(x) for x in args.gpus.split(",")]:
             "wall_input_GBps": round(args.bytes / best / 1e9, 2),
             "pipeline_seconds": None if best_pipe is None else round(best_pipe, 3),
             "pipeline_input_GBps": None if not best_pipe else round(args.bytes / best_pipe / 1e9, 2),
-            "note": "wall = whole `blt` process incl. CUDA context creation (0.7-6 s on these boxes); pipeline = mmap -> pinned -> H2D -> kernel -> D2H -> mapped output, from the stage log; tmpfs"}
+            "note": "wall = whole `blt` process incl. CUDA context creation (0.7-6 s on these boxes); pipeline = mmap -> pinned -> H2D -> kernel -> D2H -> mapped output -> unmap/trim and device teardown, from the stage log; tmpfs"}
     if want is not None:
         line["matches_oracle"] = hashlib.sha256(open(outp, "rb").read()).hexdigest() == want
     print(json.dumps(line), flush=True)
