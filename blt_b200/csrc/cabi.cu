@@ -74,6 +74,7 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
     res->kind = DeviceResult::KNOWN;
     res->len = 0;
     res->sweeps = 0;
+    res->owner = nullptr;
     if (n == 0) return BLT_OK;
     if (chunk == 0 || chunk > n) chunk = n;
     if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
@@ -104,10 +105,10 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
             a.out_cap_tokens = out_cap / 2; a.out_base_tokens = 0;
             a.chunk_ends = d_chunk_ends; a.chunk_ends_base = 0;
             a.scratch = ws.scratch;
-            CUDA_TRY(bltk::launch_bpe_sweep_pairs(a, s->d_table, s->variant, s->try_dense, stream));
+            CUDA_TRY(bltk::launch_bpe_sweep_pairs(a, s->d_table, s->variant, s->want_dense(), stream, &res->launches));
+            res->owner = (res->launches == bltk::kLaunchesDenseAttempt) ? s : nullptr;
             res->kind = DeviceResult::IN_SCRATCH;
             res->sweeps = 1;  // byte keys, ids >= 256: the reference's 2nd sweep cannot merge
-            res->launches = 1;
             return BLT_OK;
         }
         case Mode::BpeGeneral: {
@@ -182,11 +183,37 @@ int finish_result(Workspace &ws, cudaStream_t stream, DeviceResult *res) {
 }
 int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res) {
     const uint32_t overflow = reinterpret_cast<const uint32_t *>(h_ctrl)[4];
+    if (overflow == 2u) return fail(BLT_ERR_CUDA, "device-side launch of the exact sweep was refused");
     if (overflow) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+    if (res->owner) {  // the dense pass was attempted: tell the predictor how it went
+        res->owner->dense_feedback(reinterpret_cast<const uint32_t *>(h_ctrl)[5] != 0u);
+        res->owner = nullptr;
+    }
     res->len = size_t(h_ctrl[0]) * 2;
     res->kind = DeviceResult::KNOWN;
     return BLT_OK;
 }
+
+}  // namespace bltc
+
+bool blt_strategy::want_dense() {
+    if (!try_dense) return false;
+    if (dense_always) return true;
+    const uint32_t k = dense_skip.load(std::memory_order_relaxed);
+    if (k != 0) { dense_skip.store(k - 1, std::memory_order_relaxed); return false; }
+    // a probe: until it is known to have succeeded, assume it fails like the last one did
+    dense_skip.store(dense_backoff.load(std::memory_order_relaxed), std::memory_order_relaxed);
+    return true;
+}
+void blt_strategy::dense_feedback(bool failed) {
+    if (!failed) { dense_backoff.store(0, std::memory_order_relaxed); dense_skip.store(0, std::memory_order_relaxed); return; }
+    const uint32_t b = dense_backoff.load(std::memory_order_relaxed);
+    const uint32_t nb = b ? std::min(2 * b, 1024u) : 16u;
+    dense_backoff.store(nb, std::memory_order_relaxed);
+    dense_skip.store(nb, std::memory_order_relaxed);
+}
+
+namespace bltc {
 
 // ---- strategy construction ------------------------------------------------------------------------
 static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **out) {
@@ -231,7 +258,10 @@ static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **ou
     }
     // tuning / test switches: tile size of the exact sweep, and whether the dense pass runs in front of it
     if (const char *v = getenv("BLT_SWEEP_VARIANT")) s->variant = atoi(v);
-    if (const char *v = getenv("BLT_DENSE")) s->try_dense = (atoi(v) != 0);
+    if (const char *v = getenv("BLT_DENSE")) {  // 0 = never, always = on every call, else the predictor decides
+        s->dense_always = std::string(v) == "always";
+        s->try_dense = s->dense_always || atoi(v) != 0;
+    }
     *out = s.release();
     return BLT_OK;
 }

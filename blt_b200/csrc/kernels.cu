@@ -262,6 +262,51 @@ struct HashFE {
 };
 
 // ================================================================================================
+// Tile bookkeeping shared by the exact sweep kernels (sweep3.cuh).
+// ================================================================================================
+struct TileInfo {
+    unsigned long long rem0;   // tile_base % chunk (tile_base itself when there are no walls)
+    unsigned long long ck0;    // tile_base / chunk
+};
+
+template <int SEG>
+struct Walls {
+    uint32_t endm;            // chunk-last positions inside the segment (incl. the last element n-1)
+    unsigned long long ck;    // chunk index of the segment's first element
+};
+
+// Which positions of the segment at element offset `off` of the tile are chunk-last.
+template <int SEG, int TILE_ELEMS>
+__device__ __forceinline__ Walls<SEG> seg_walls(const SweepArgs &a, const TileInfo &ti, uint32_t off,
+                                                unsigned long long g) {
+    Walls<SEG> w;
+    w.endm = 0;
+    w.ck = 0;
+    if (a.chunk != 0) {
+        if (a.chunk >= size_t(TILE_ELEMS)) {  // at most one wall per tile
+            unsigned long long rem = ti.rem0 + off;
+            w.ck = ti.ck0;
+            if (rem >= a.chunk) { rem -= a.chunk; w.ck += 1; }
+            const unsigned long long d = a.chunk - 1 - rem;
+            if (d < SEG) w.endm = 1u << uint32_t(d);
+        } else {  // tiny chunks (tests): walk the segment
+            const uint32_t c = uint32_t(a.chunk);
+            const uint32_t lin = uint32_t(ti.rem0) + off;
+            w.ck = ti.ck0 + lin / c;
+            uint32_t r = lin % c;
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) {
+                if (++r == c) { w.endm |= 1u << j; r = 0; }
+            }
+        }
+    }
+    if (g < a.n && a.n - 1 - g < SEG) w.endm |= 1u << uint32_t(a.n - 1 - g);  // end of the last chunk
+    return w;
+}
+
+#include "sweep3.cuh"
+
+// ================================================================================================
 // K2-dense: the speculative streaming form of the sweep for merge-dense input.
 //
 // If every pair that starts at an EVEN offset of its chunk is a rule, the reference's scan merges
@@ -273,13 +318,18 @@ struct HashFE {
 // always enqueued behind it and returns at once when the hypothesis held.
 // ================================================================================================
 __global__ void __launch_bounds__(kCtaThreads, 1)
-dense_pairs_kernel(const unsigned char *__restrict__ in, unsigned long long n, uint16_t *__restrict__ out,
-                   const uint16_t *__restrict__ table, uint32_t *abort_flag, uint32_t *work_counter) {
+dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int variant, unsigned exact_grid) {
     extern __shared__ __align__(16) unsigned char smem[];
     PairsFE fe;
     PairsFE::Params p{table};
     fe.init(p, smem);
     __syncthreads();
+    const unsigned char *__restrict__ in = static_cast<const unsigned char *>(a.in);
+    const unsigned long long n = a.n;
+    uint16_t *__restrict__ out = a.out + a.out_base_tokens;
+    uint32_t *const work_counter = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(a.scratch.ctrl) + 256);
+    uint32_t *const done_counter = work_counter + 1;
+    uint32_t *const abort_flag = a.scratch.dense_abort;
     // Work is handed out per warp in units of kDenseUnitSegs consecutive 16-byte segments: the first unit
     // of a warp is static, the following ones come from one global counter (an SM that gets less memory
     // bandwidth than its neighbours simply takes fewer units; with a static split the slowest SM set the
@@ -356,53 +406,48 @@ dense_pairs_kernel(const unsigned char *__restrict__ in, unsigned long long n, u
         if (i < n) out[i / 2] = uint16_t(uint32_t(in[i]) << 8);  // odd length: the last element stays a raw token
     }
     // one store per CTA: 150 000 threads storing to one word serialise in L2 for tens of microseconds
-    if (__syncthreads_or(bad) && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(abort_flag) = 1u;
-}
-
-// ================================================================================================
-// Tile bookkeeping shared by the exact sweep kernels (sweep3.cuh).
-// ================================================================================================
-struct TileInfo {
-    unsigned long long rem0;   // tile_base % chunk (tile_base itself when there are no walls)
-    unsigned long long ck0;    // tile_base / chunk
-};
-
-template <int SEG>
-struct Walls {
-    uint32_t endm;            // chunk-last positions inside the segment (incl. the last element n-1)
-    unsigned long long ck;    // chunk index of the segment's first element
-};
-
-// Which positions of the segment at element offset `off` of the tile are chunk-last.
-template <int SEG, int TILE_ELEMS>
-__device__ __forceinline__ Walls<SEG> seg_walls(const SweepArgs &a, const TileInfo &ti, uint32_t off,
-                                                unsigned long long g) {
-    Walls<SEG> w;
-    w.endm = 0;
-    w.ck = 0;
-    if (a.chunk != 0) {
-        if (a.chunk >= size_t(TILE_ELEMS)) {  // at most one wall per tile
-            unsigned long long rem = ti.rem0 + off;
-            w.ck = ti.ck0;
-            if (rem >= a.chunk) { rem -= a.chunk; w.ck += 1; }
-            const unsigned long long d = a.chunk - 1 - rem;
-            if (d < SEG) w.endm = 1u << uint32_t(d);
-        } else {  // tiny chunks (tests): walk the segment
-            const uint32_t c = uint32_t(a.chunk);
-            const uint32_t lin = uint32_t(ti.rem0) + off;
-            w.ck = ti.ck0 + lin / c;
-            uint32_t r = lin % c;
-#pragma unroll
-            for (int j = 0; j < SEG; ++j) {
-                if (++r == c) { w.endm |= 1u << j; r = 0; }
-            }
+    __shared__ uint32_t s_last;
+    const bool cta_bad = __syncthreads_or(bad) != 0;
+    if (threadIdx.x == 0) {
+        if (cta_bad) *reinterpret_cast<volatile uint32_t *>(abort_flag) = 1u;
+        __threadfence();
+        s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last == 0) return;
+    // ---- the last CTA to finish: everybody else's stores (output and abort word) are visible ----
+    __threadfence();
+    const bool failed = *reinterpret_cast<volatile uint32_t *>(abort_flag) != 0u;
+    if (!failed) {  // the speculation held: the output is complete, publish the totals of the sweep
+        const unsigned long long tokens = (n + 1) / 2;
+        if (threadIdx.x == 0) {
+            *a.scratch.total_tokens = tokens;
+            *a.scratch.merged_any = (n >= 2) ? 1u : 0u;
+            *a.scratch.overflow = 0u;
+            reinterpret_cast<uint32_t *>(a.scratch.ctrl)[5] = 0u;  // "dense pass failed" (read by the host's predictor)
+        }
+        if (a.chunk_ends != nullptr) {
+            const unsigned long long c = (a.chunk == 0 || a.chunk > n) ? n : a.chunk;
+            const unsigned long long n_chunks = (n + c - 1) / c;
+            for (unsigned long long k = threadIdx.x; k < n_chunks; k += blockDim.x)
+                a.chunk_ends[k] = a.chunk_ends_base + ((k + 1 == n_chunks) ? 2 * tokens : (k + 1) * c);
+        }
+    } else {
+        // Some even pair is not a rule: the exact sweep redoes the launch.  It is enqueued from here (tail
+        // launch: it starts when this grid has completed) so that the host never enqueues - and the GPU never
+        // schedules - three kernels that would have nothing to do in the common case.
+        if (threadIdx.x < 64) reinterpret_cast<uint32_t *>(a.scratch.ctrl)[threadIdx.x] = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            reinterpret_cast<uint32_t *>(a.scratch.ctrl)[5] = 1u;
+            __threadfence();
+            const bool ok = (variant == 1) ? tail_launch_sweep3<PairsFE, 8>(a, p, exact_grid)
+                                           : tail_launch_sweep3<PairsFE, 4>(a, p, exact_grid);
+            if (!ok) *a.scratch.overflow = 2u;  // reported as a CUDA error by the host (never seen so far)
         }
     }
-    if (g < a.n && a.n - 1 - g < SEG) w.endm |= 1u << uint32_t(a.n - 1 - g);  // end of the last chunk
-    return w;
 }
 
-#include "sweep3.cuh"
 
 }  // namespace
 
@@ -457,11 +502,9 @@ static const char *kVariantNames[] = {"r4", "r8"};
 int num_sweep_variants() { return int(sizeof(kVariantNames) / sizeof(kVariantNames[0])); }
 const char *sweep_variant_name(int v) { return (v >= 0 && v < num_sweep_variants()) ? kVariantNames[v] : "?"; }
 
-cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a_in, const uint16_t *d_table, int variant, bool dense_enabled,
-                                   cudaStream_t stream) {
+cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, int variant, bool dense_enabled,
+                                   cudaStream_t stream, int *host_launches) {
     PairsFE::Params p{d_table};
-    SweepArgs a = a_in;
-    a.dense_flag = nullptr;
     // Dense speculation is sound when no even pair can straddle a wall (even chunk size, or one chunk), the
     // output starts on a 16-byte boundary and the output surely fits.
     const size_t chunk = (a.chunk == 0 || a.chunk > a.n) ? a.n : a.chunk;
@@ -478,21 +521,25 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a_in, const uint16_t *d_tabl
             if (err != cudaSuccess) return err;
             configured[dev].store(true, std::memory_order_release);
         }
-        // the exact launch below zeroes the control block too; the abort word must be clear before the dense pass
-        // (one memset: work counter at +256, abort word at +384)
+        // the exact kernels are launched from the device if the speculation fails: they must be configured too
+        unsigned exact_grid = 0;
+        if (variant == 1) { err = Sweep3Launch<PairsFE, 8>::configure(dev); exact_grid = Sweep3Launch<PairsFE, 8>::grid_for(a.n, dev); }
+        else { err = Sweep3Launch<PairsFE, 4>::configure(dev); exact_grid = Sweep3Launch<PairsFE, 4>::grid_for(a.n, dev); }
+        if (err != cudaSuccess) return err;
+        if (a.scratch.max_tiles < size_t(2 * kMaxRanges)) return cudaErrorInvalidValue;
+        // work counter (+256), done counter (+260) and abort word (+384) of the dense pass
         err = cudaMemsetAsync(static_cast<unsigned char *>(a.scratch.ctrl) + 256, 0, 132, stream);
         if (err != cudaSuccess) return err;
         const size_t units = a.n / 16 / kDenseUnitSegs;
         size_t grid = (units + kCtaThreads / 32 - 1) / (kCtaThreads / 32);
         if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
         if (grid == 0) grid = 1;
-        dense_pairs_kernel<<<dim3(unsigned(grid)), dim3(kCtaThreads), PairsFE::TABLE_BYTES, stream>>>(
-            static_cast<const unsigned char *>(a.in), a.n, a.out + a.out_base_tokens, d_table, a.scratch.dense_abort,
-            reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(a.scratch.ctrl) + 256));
-        err = cudaGetLastError();
-        if (err != cudaSuccess) return err;
-        a.dense_flag = a.scratch.dense_abort;
+        dense_pairs_kernel<<<dim3(unsigned(grid)), dim3(kCtaThreads), PairsFE::TABLE_BYTES, stream>>>(a, d_table, variant,
+                                                                                                  exact_grid);
+        if (host_launches) *host_launches = kLaunchesDenseAttempt;
+        return cudaGetLastError();
     }
+    if (host_launches) *host_launches = kLaunchesExact;
     switch (variant) {
         case 1: return launch_sweep3<PairsFE, 8>(a, p, stream);
         default: return launch_sweep3<PairsFE, 4>(a, p, stream);

@@ -70,7 +70,6 @@ struct SweepArgs {
     size_t out_base_tokens;  // the first token of this sweep lands at out[out_base_tokens]
     uint64_t *chunk_ends;    // optional device array: inclusive prefix of OUTPUT BYTES per chunk
     size_t chunk_ends_base;  // bytes added to every chunk_ends entry (output before this launch)
-    const uint32_t *dense_flag;  // non-null: a dense pass ran first; *dense_flag == 0 means it succeeded
     SweepScratch scratch;
 };
 
@@ -80,14 +79,16 @@ cudaError_t launch_widen(const uint8_t *d_in, size_t n, uint8_t *d_out, cudaStre
 cudaError_t launch_fill_chunk_ends(uint64_t *d_ends, size_t n, size_t chunk, unsigned bytes_per_elem,
                                    cudaStream_t stream);
 // K2.  d_table = kPairTableEntries u16 in device memory (layout above).
-// try_dense: enqueue the speculative dense pass in front of the exact sweep.
+// try_dense: run the speculative dense pass, which launches the exact sweep itself if it must.
+// *host_launches (optional) receives the number of kernels the host enqueued.
 cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, int variant, bool try_dense,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, int *host_launches = nullptr);
 // K3.  in_is_u16: input is BE u16 tokens (true) or raw bytes (false).
 cudaError_t launch_bpe_sweep_hash(const SweepArgs &a, const HashTableView &t, bool in_is_u16,
                                   cudaStream_t stream);
-// Kernels enqueued per K2 call: dense_pairs_kernel + count + scan + emit (bench.py's gpu_launches claim).
-constexpr int kLaunchesPerSweep = 4;
+// Kernels the HOST enqueues per K2 call: the dense pass alone when it is attempted (it launches count, scan
+// and emit itself, from the device, only if its speculation fails); count + scan + emit otherwise.
+constexpr int kLaunchesDenseAttempt = 1, kLaunchesExact = 3;
 
 int num_sweep_variants();
 const char *sweep_variant_name(int variant);

@@ -5,6 +5,7 @@
 #include "host_config.h"
 #include "kernels.cuh"
 
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -34,7 +35,8 @@ struct DeviceResult {
     enum Kind { KNOWN, IN_SCRATCH } kind = KNOWN;  // IN_SCRATCH: length still in device memory
     size_t len = 0;       // output bytes
     uint32_t sweeps = 0;  // productive + verifying sweeps actually launched
-    int launches = 0;     // kernels enqueued
+    int launches = 0;     // kernels enqueued by the host
+    blt_strategy *owner = nullptr;  // set when the dense pass was attempted: decode_ctrl reports back to it
 };
 
 int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, size_t chunk, uint8_t *d_out,
@@ -89,6 +91,13 @@ struct blt_strategy {
     uint32_t hash_mask = 0;
     int variant = 0;                      // K2 tile configuration of the exact sweep
     bool try_dense = true;                // K2: run the speculative dense pass first
+    // Predictor of the speculation.  A failed attempt costs the attempt plus a device-side launch of the
+    // exact sweep (~0.1 ms), so after a failure the next `backoff` calls go to the exact sweep directly
+    // (16, doubling to 1024 while the probes keep failing); one success makes every call dense again.
+    std::atomic<uint32_t> dense_skip{0}, dense_backoff{0};
+    bool dense_always = false;            // BLT_DENSE=always: attempt on every call (tests)
+    bool want_dense();
+    void dense_feedback(bool failed);
     std::mutex resident_mu;
     bltc::Workspace resident;             // workspace of blt_process_resident
     bltc::DeviceResult resident_result;

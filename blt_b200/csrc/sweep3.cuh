@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a
     using C = Sweep3Cfg<FE, R>;
     constexpr int SEG = C::SEG;
     constexpr uint32_t ALL = C::ALL;
-    if (a.dense_flag != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.dense_flag) == 0u) return;
     extern __shared__ __align__(16) unsigned char smem[];
     FE fe;
     fe.init(fp, smem);
@@ -225,21 +224,6 @@ constexpr int kScanItems = kMaxRanges / kCtaThreads;  // ranges per thread
 
 // One CTA.  tile_status[w] = (carry entering warp w's range) << 63 | tokens emitted by ranges 0..w-1.
 __global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a, int n_ranges) {
-    if (a.dense_flag != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.dense_flag) == 0u) {
-        // the dense pass in front of this launch already produced the whole output: publish its totals
-        const unsigned long long tokens = (a.n + 1) / 2;
-        if (threadIdx.x == 0) {
-            *a.scratch.total_tokens = tokens;
-            *a.scratch.merged_any = (a.n >= 2) ? 1u : 0u;
-        }
-        if (a.chunk_ends != nullptr) {
-            const unsigned long long c = (a.chunk == 0 || a.chunk > a.n) ? a.n : a.chunk;
-            const unsigned long long n_chunks = (a.n + c - 1) / c;
-            for (unsigned long long k = threadIdx.x; k < n_chunks; k += blockDim.x)
-                a.chunk_ends[k] = a.chunk_ends_base + ((k + 1 == n_chunks) ? 2 * tokens : (k + 1) * c);
-        }
-        return;
-    }
     __shared__ ScanFn warp_agg[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int t0 = threadIdx.x * kScanItems;
@@ -306,7 +290,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
     constexpr int SEG = C::SEG;
     constexpr int HV = C::HV;
     constexpr uint32_t ALL = C::ALL;
-    if (a.dense_flag != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.dense_flag) == 0u) return;
     extern __shared__ __align__(16) unsigned char smem[];
     FE fe;
     fe.init(fp, smem);
@@ -463,37 +446,63 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
 }
 
 template <class FE, int R>
-cudaError_t launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, cudaStream_t stream) {
+struct Sweep3Launch {
     using C = Sweep3Cfg<FE, R>;
-    constexpr size_t smem_count = FE::TABLE_BYTES;
-    constexpr size_t smem_emit = FE::TABLE_BYTES + size_t(kCtaThreads / 32) * C::STAGE_TOKENS * 2;
+    static constexpr size_t smem_count = FE::TABLE_BYTES;
+    static constexpr size_t smem_emit = FE::TABLE_BYTES + size_t(kCtaThreads / 32) * C::STAGE_TOKENS * 2;
     static_assert(smem_emit <= 227 * 1024, "shared memory budget");
-    auto kc = count_kernel<FE, R>;
-    auto ke = emit_kernel<FE, R>;
-    static std::atomic<bool> configured[kMaxDevices];
+    // opt the two big kernels into their dynamic shared memory (once per device; also what a device-side
+    // launch of them relies on)
+    static cudaError_t configure(int dev) {
+        static std::atomic<bool> configured[kMaxDevices];
+        if (dev >= kMaxDevices) return cudaErrorInvalidDevice;
+        if (!configured[dev].load(std::memory_order_acquire)) {
+            cudaError_t err = cudaFuncSetAttribute(count_kernel<FE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_count));
+            if (err != cudaSuccess) return err;
+            err = cudaFuncSetAttribute(emit_kernel<FE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_emit));
+            if (err != cudaSuccess) return err;
+            configured[dev].store(true, std::memory_order_release);
+        }
+        return cudaSuccess;
+    }
+    static unsigned grid_for(size_t n, int dev) {
+        const size_t n_tiles = (n + C::TILE_ELEMS - 1) / C::TILE_ELEMS;
+        const size_t warps_per_cta = kCtaThreads / 32;
+        size_t grid = (n_tiles + warps_per_cta - 1) / warps_per_cta;
+        if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
+        if (grid > size_t(kMaxRanges) / warps_per_cta) grid = size_t(kMaxRanges) / warps_per_cta;
+        if (grid == 0) grid = 1;
+        return unsigned(grid);
+    }
+};
+
+// Host launch: control block cleared, then count, scan, emit on `stream`.
+template <class FE, int R>
+cudaError_t launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, cudaStream_t stream) {
+    using L = Sweep3Launch<FE, R>;
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
-    if (dev >= kMaxDevices) return cudaErrorInvalidDevice;
-    if (!configured[dev].load(std::memory_order_acquire)) {
-        err = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_count));
-        if (err != cudaSuccess) return err;
-        err = cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_emit));
-        if (err != cudaSuccess) return err;
-        configured[dev].store(true, std::memory_order_release);
-    }
-    if (a.scratch.max_tiles < size_t(2 * kMaxRanges)) return cudaErrorInvalidValue;
-    // (the dense-abort word at ctrl+384 belongs to the dense pass enqueued in front of this launch: keep it)
-    err = cudaMemsetAsync(a.scratch.ctrl, 0, 384, stream);
+    err = L::configure(dev);
     if (err != cudaSuccess) return err;
-    const size_t n_tiles = (a.n + C::TILE_ELEMS - 1) / C::TILE_ELEMS;
-    const size_t warps_per_cta = kCtaThreads / 32;
-    size_t grid = (n_tiles + warps_per_cta - 1) / warps_per_cta;
-    if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
-    if (grid > size_t(kMaxRanges) / warps_per_cta) grid = size_t(kMaxRanges) / warps_per_cta;
-    if (grid == 0) grid = 1;
-    kc<<<dim3(unsigned(grid)), dim3(kCtaThreads), smem_count, stream>>>(a, fp);
-    scan_kernel<<<1, kCtaThreads, 0, stream>>>(a, int(grid * warps_per_cta));
-    ke<<<dim3(unsigned(grid)), dim3(kCtaThreads), smem_emit, stream>>>(a, fp);
+    if (a.scratch.max_tiles < size_t(2 * kMaxRanges)) return cudaErrorInvalidValue;
+    err = cudaMemsetAsync(a.scratch.ctrl, 0, 256, stream);
+    if (err != cudaSuccess) return err;
+    const unsigned grid = L::grid_for(a.n, dev);
+    count_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_count, stream>>>(a, fp);
+    scan_kernel<<<1, kCtaThreads, 0, stream>>>(a, int(grid * (kCtaThreads / 32)));
+    emit_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, stream>>>(a, fp);
     return cudaGetLastError();
+}
+
+// Device launch (CUDA dynamic parallelism, tail-launch stream): the same three kernels, enqueued by the dense
+// pass when its speculation failed.  They start when the launching grid has completed and run in order.
+// The caller has cleared the control block.  Returns false if a launch was refused.
+template <class FE, int R>
+__device__ bool tail_launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, unsigned grid) {
+    using L = Sweep3Launch<FE, R>;
+    count_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_count, cudaStreamTailLaunch>>>(a, fp);
+    scan_kernel<<<1, kCtaThreads, 0, cudaStreamTailLaunch>>>(a, int(grid * (kCtaThreads / 32)));
+    emit_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, cudaStreamTailLaunch>>>(a, fp);
+    return cudaGetLastError() == cudaSuccess;
 }

@@ -119,11 +119,12 @@ def _random_case(rng, n, alphabet, density):
     return np.ascontiguousarray(data), pairs
 
 
-@pytest.mark.parametrize("variant,dense", [(0, True), (1, True), (0, False), (1, False)])
+@pytest.mark.parametrize("variant,dense", [(0, "always"), (1, "always"), (0, "0"), (1, "0"), (0, "1")])
 def test_random_vs_oracle_all_variants(nat, torch_mod, oracle, variant, dense, monkeypatch):
-    """Both tile sizes of the exact sweep, with and without the dense speculative pass in front."""
+    """Both tile sizes of the exact sweep; the dense speculative pass attempted on every call (its failure
+    launches the exact sweep from the device), never, or as the predictor decides (the default)."""
     monkeypatch.setenv("BLT_SWEEP_VARIANT", str(variant))
-    monkeypatch.setenv("BLT_DENSE", "1" if dense else "0")
+    monkeypatch.setenv("BLT_DENSE", dense)
     c = nat.Context(0)
     rng = random.Random(1000 + variant)
     sizes = [1, 2, 15, 16, 17, 255, 4095, 4096, 4097, 8191, 8193, 16384, 65537, 300001, 1 * MiB + 3, 5 * MiB + 11]
@@ -152,6 +153,24 @@ def test_random_vs_oracle_all_variants(nat, torch_mod, oracle, variant, dense, m
             assert np.array_equal(got, oracle.run_buffer("bpe", data, 65536, 4, om))
             s.close()
     c.close()
+
+
+def test_dense_predictor_sequence(ctx, torch_mod, oracle):
+    """One strategy, inputs that flip between merge-dense and sparse: whichever path the predictor picks
+    (dense attempt, device-launched exact sweep, host-launched exact sweep), the bytes are the oracle's."""
+    pairs = {(97, 98): 256, (98, 97): 257, (97, 97): 258, (98, 98): 259}
+    om = oracle.Merges(pairs)
+    s = ctx.bpe_from_pairs(pairs)
+    rng = np.random.default_rng(7)
+    n = 1 * MiB + 64
+    dense_in = rng.integers(97, 99, size=n, dtype=np.uint8)             # every pair is a rule
+    sparse_in = rng.integers(97, 101, size=n, dtype=np.uint8)           # c, d break the runs
+    want = {True: oracle.run_buffer("bpe", dense_in, 65536, 4, om), False: oracle.run_buffer("bpe", sparse_in, 65536, 4, om)}
+    plan = [True] * 3 + [False] * 40 + [True] * 40 + [False, True] * 10
+    for i, d in enumerate(plan):
+        got, _ = resident(torch_mod, s, dense_in if d else sparse_in, 65536)
+        assert np.array_equal(got, want[d]), (i, d)
+    s.close()
 
 
 def test_long_runs_and_carry_chains(ctx, torch_mod, oracle):
