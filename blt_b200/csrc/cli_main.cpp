@@ -1,5 +1,5 @@
 // cli_main.cpp -- the `blt` command line of the reference (src/main.rs:8-106) over libblt_cuda.so.
-// Same flags, same defaults, same exit behaviour; one addition: --gpus N (default: all visible).
+// Same flags, same defaults, same exit behaviour; one addition: --gpus N (default: 1).
 #include "../../include/blt_cuda.h"
 
 #include <cstdio>
@@ -22,7 +22,7 @@ const char *kHelp =
     "      --threads <NUM>       Override worker count (default: auto based on cores)\n"
     "      --memcap <PERCENT>    Max RAM usage fraction (e.g., 70 for 70%)\n"
     "      --chunksize <SIZE>    Min/Max chunk size (e.g. 4MB, 256KB).\n"
-    "      --gpus <NUM>          GPUs to shard chunks over (default: all visible)\n"
+    "      --gpus <NUM>          GPUs to shard chunks over (default: 1; every extra GPU costs ~1 s of CUDA start-up)\n"
     "  -h, --help                Print help\n"
     "  -V, --version             Print version\n";
 
@@ -138,6 +138,13 @@ int main(int argc, char **argv) {
     cfg.memcap = unsigned(memcap);
     cfg.passthrough = passthrough;
     cfg.num_gpus = int(gpus);
+    // CUDA start-up time grows with the number of devices the driver has to open (about a second each on an
+    // 8-GPU box): unless the user chose the devices, expose only the ones this run will use.
+    if (getenv("CUDA_VISIBLE_DEVICES") == nullptr) {
+        std::string vis;
+        for (unsigned long long g = 0; g < (gpus ? gpus : 1); ++g) vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+    }
     const int rc = blt_run_tokenizer(&cfg);
     if (rc != BLT_OK) {  // main.rs:100-103
         std::fprintf(stderr, "Error running tokenizer: %s\n", blt_last_error());

@@ -575,7 +575,9 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     int rc = blt_device_count(&n_dev);
     slog.mark("device count");
     if (rc) { cleanup(); return rc; }  // no CPU fallback
-    int n_gpus = cfg->num_gpus > 0 ? std::min(cfg->num_gpus, n_dev) : n_dev;
+    // default: one GPU.  The host side (page cache, PCIe) bounds file-to-file long before one B200 does, and
+    // every further context costs about a second of start-up (host pipeline).
+    int n_gpus = cfg->num_gpus > 0 ? std::min(cfg->num_gpus, n_dev) : 1;
     if (!of.seekable) n_gpus = 1;  // a stream can only be written front to back
 
     if (!in_is_file) {

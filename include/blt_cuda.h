@@ -135,7 +135,7 @@ typedef struct blt_core_config {
     int has_memcap;           /* Option<u8>: 0 = None -> 80 (lib.rs:170)                              */
     unsigned memcap;          /*   percent of RAM for the automatic chunk size (chunking.rs:41-42)    */
     int passthrough;          /* bool (lib.rs:129)                                                    */
-    int num_gpus;             /* NEW: GPUs to shard chunks over; 0 = all visible                      */
+    int num_gpus;             /* NEW: GPUs to shard chunks over; 0 = one (each costs ~1 s of start-up) */
 } blt_core_config;
 
 /* run_tokenizer(CoreConfig::new_from_cli(...)) (lib.rs:149-174, 245-267): parse + load merges, pick

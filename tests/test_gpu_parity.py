@@ -365,6 +365,50 @@ def test_config3_and_4_one_gib(ctx, torch_mod, oracle, tmp_path, cfg):
 
 # ---- file to file: CLI and Python binding -------------------------------------------------------------------
 
+def test_resident_beyond_4gib(ctx, torch_mod, oracle):
+    """More than 2^32 input bytes in one launch (every index on the device path is 64-bit): basic, the
+    exact sweep (sparse table) and the dense pass (full table), checked on the chunks around the 4 GiB
+    mark and on the ragged last chunk."""
+    from blt_b200 import synth
+    torch = torch_mod
+    chunk = 16 * MiB
+    n = (4 << 30) + 3 * chunk + 12345
+    n_chunks = (n + chunk - 1) // chunk
+    data = synth.text(n, 0xB170099)
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.empty(2 * n + 16, dtype=torch.uint8, device="cuda")
+    d_ends = torch.zeros(n_chunks, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    which = [0, 127, 254, 255, 256, 257, n_chunks - 2, n_chunks - 1]
+
+    def run(strat):
+        out_len = strat.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), 2 * n, d_ends.data_ptr(), stream)
+        ends = d_ends.cpu().numpy()
+        assert int(ends[-1]) == out_len
+        return out_len, ends
+
+    def chunk_bytes(ends, k):
+        lo = 0 if k == 0 else int(ends[k - 1])
+        return d_out[lo:int(ends[k])].cpu().numpy()
+
+    out_len, ends = run(ctx.basic())
+    assert out_len == 2 * n
+    for k in which:
+        want = np.frombuffer(oracle.process_chunk("basic", data[k * chunk:(k + 1) * chunk], None), dtype=np.uint8)
+        assert np.array_equal(chunk_bytes(ends, k), want), ("basic", k)
+    for rules in (256, 32768):
+        l, r = synth.merges_from_sample(data[: 64 * MiB], rules)
+        pairs = {(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))}
+        om = oracle.Merges(pairs)
+        s = ctx.bpe_from_pairs(pairs)
+        out_len, ends = run(s)
+        assert np.all(np.diff(ends) > 0)
+        for k in which:
+            want = np.frombuffer(oracle.process_chunk("bpe", data[k * chunk:(k + 1) * chunk], om), dtype=np.uint8)
+            assert np.array_equal(chunk_bytes(ends, k), want), (rules, k)
+        s.close()
+
+
 def test_cli_file_to_file_and_stdin(oracle, tmp_path):
     from blt_b200 import synth
     data = synth.text(5 * MiB + 321, 4242)

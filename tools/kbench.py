@@ -34,6 +34,39 @@ def time_resident(strat, d_in, n, chunk, d_out, iters):
     return out_len, ms[len(ms) // 2], ms[0]
 
 
+def general_map(peak):
+    """K3: a map merges.txt cannot express (second-level rules on produced ids) -> hash front end, several
+    sweeps per chunk with a host round trip after each (SURVEY.md 8d, config 4's 64 MiB slice)."""
+    import time
+    n, chunk = 64 << 20, 16 << 20
+    data = synth.text(n, synth.SEED_CONFIG[4])
+    l, r = synth.merges_from_sample(data, 256)
+    pairs = {(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))}
+    for i in range(64):
+        pairs[(256 + i, 32)] = 1000 + i        # (merged id, space) -> second-level id
+        pairs[(1000 + i, 256 + i)] = 2000 + i  # third level
+    ctx = nat.Context(0)
+    strat = ctx.bpe_from_pairs(pairs)
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    times = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out_len = strat.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), d_out.numel(), 0, stream, sync=True)
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    _, sweeps = strat.resident_result(stream)
+    med = sorted(times)[len(times) // 2]
+    alg = n + out_len
+    print(json.dumps({"config": "general map (K3, hash front end)", "n": n, "rules": len(pairs), "sweeps": sweeps, "out_bytes": out_len,
+                      "ms_median_wall": round(med, 3), "input_GBps": round(n / med / 1e6, 1),
+                      "algorithmic_GBps": round(alg / med / 1e6, 1), "frac_of_measured_hbm": round(alg / med / 1e6 / peak, 4)}), flush=True)
+    strat.close()
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bytes", type=int, default=1 << 30)
@@ -49,6 +82,9 @@ def main():
     torch.cuda.set_device(0)
     d_out = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
     for cfg in [int(c) for c in args.configs.split(",")]:
+        if cfg == 6:
+            general_map(peak)
+            continue
         if cfg == 1:
             data = synth.random_bytes(n, synth.SEED_CONFIG[1])
         elif cfg == 4:
