@@ -62,6 +62,8 @@ def lib():
     L.blt_tokenize_host.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp, C.c_size_t, szp]
     L.blt_process_resident.argtypes = [vp, vp, C.c_size_t, C.c_size_t, vp, C.c_size_t, vp, vp, szp]
     L.blt_resident_result.argtypes = [vp, vp, szp, C.POINTER(C.c_uint32)]
+    L.blt_detokenize_host.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, szp]
+    L.blt_detokenize_resident.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, szp]
     L.blt_run_tokenizer.argtypes = [C.POINTER(CoreConfig)]
     L.blt_load_bpe_merges.argtypes = [C.c_char_p, u16p, u16p, u16p, C.c_size_t, szp]
     L.blt_parse_chunk_size.argtypes = [C.c_char_p, szp]
@@ -189,6 +191,23 @@ class Strategy:
         n_out = C.c_size_t()
         check(lib().blt_process_resident(self._h, d_in, n, chunk_size, d_out, out_cap, d_chunk_ends or None,
                                          stream or None, C.byref(n_out) if sync else None))
+        return n_out.value if sync else None
+
+    def detokenize_host(self, tokens, has_content_type: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Big-endian u16 tokens (as written by tokenize_host / the CLI) back to bytes."""
+        a = _as_u8(tokens)
+        if out is None:
+            out = np.empty(max(a.size, 1), dtype=np.uint8)
+        n_out = C.c_size_t()
+        check(lib().blt_detokenize_host(self._h, a.ctypes.data, a.size, 1 if has_content_type else 0, out.ctypes.data,
+                                        out.size, C.byref(n_out)))
+        return out[: n_out.value]
+
+    def detokenize_resident(self, d_tokens: int, n_bytes: int, d_out: int, out_cap: int, stream: int = 0,
+                            sync: bool = True) -> Optional[int]:
+        n_out = C.c_size_t()
+        check(lib().blt_detokenize_resident(self._h, d_tokens, n_bytes, d_out, out_cap, stream or None,
+                                            C.byref(n_out) if sync else None))
         return n_out.value if sync else None
 
     def resident_result(self, stream: int = 0) -> Tuple[int, int]:

@@ -75,6 +75,7 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
     res->len = 0;
     res->sweeps = 0;
     res->owner = nullptr;
+    res->len_scale = 2;
     if (n == 0) return BLT_OK;
     if (chunk == 0 || chunk > n) chunk = n;
     if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
@@ -189,8 +190,48 @@ int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res) {
         res->owner->dense_feedback(reinterpret_cast<const uint32_t *>(h_ctrl)[5] != 0u);
         res->owner = nullptr;
     }
-    res->len = size_t(h_ctrl[0]) * 2;
+    if (res->len_scale == 1 && reinterpret_cast<const uint32_t *>(h_ctrl)[6] != 0u)
+        return fail(BLT_ERR_INVALID_DATA, "token stream contains a token that is not in the table");
+    res->len = size_t(h_ctrl[0]) * res->len_scale;
     res->kind = DeviceResult::KNOWN;
+    return BLT_OK;
+}
+
+// ---- detokenizer (no reference counterpart; see blt_cuda.h) ----------------------------------------
+int run_detok(blt_strategy *s, Workspace &ws, const uint8_t *d_tokens, size_t n_bytes, uint8_t *d_out, size_t out_cap,
+              cudaStream_t stream, DeviceResult *res) {
+    res->kind = DeviceResult::KNOWN;
+    res->len = 0;
+    res->sweeps = 0;
+    res->owner = nullptr;
+    res->len_scale = 1;
+    res->launches = 0;
+    if (n_bytes & 1) return fail(BLT_ERR_INVALID_DATA, "token stream has an odd number of bytes");
+    if (n_bytes == 0) return BLT_OK;
+    if ((reinterpret_cast<uintptr_t>(d_tokens) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
+        return fail(BLT_ERR_INVALID_INPUT, "device buffers must be 16-byte aligned");
+    if (s->mode == Mode::Passthrough) {
+        if (out_cap < n_bytes) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+        CUDA_TRY(cudaMemcpyAsync(d_out, d_tokens, n_bytes, cudaMemcpyDeviceToDevice, stream));
+        res->len = n_bytes;
+        return BLT_OK;
+    }
+    int rc = s->ensure_detok();
+    if (rc) return rc;
+    rc = ws.ensure_scratch(1);
+    if (rc) return rc;
+    bltk::DetokArgs a{};
+    a.in = reinterpret_cast<const uint16_t *>(d_tokens);
+    a.n_tok = n_bytes / 2;
+    a.out = d_out;
+    a.out_cap = out_cap;
+    a.table = s->d_detok;
+    a.limit = s->detok_limit;
+    a.holes = s->detok_holes;
+    a.scratch = ws.scratch;
+    CUDA_TRY(bltk::launch_detokenize(a, stream));
+    res->kind = DeviceResult::IN_SCRATCH;
+    res->launches = bltk::kLaunchesDetok;
     return BLT_OK;
 }
 
@@ -211,6 +252,46 @@ void blt_strategy::dense_feedback(bool failed) {
     const uint32_t nb = b ? std::min(2 * b, 1024u) : 16u;
     dense_backoff.store(nb, std::memory_order_relaxed);
     dense_skip.store(nb, std::memory_order_relaxed);
+}
+
+int blt_strategy::ensure_detok() {
+    std::lock_guard<std::mutex> lk(detok_mu);
+    const char *not_inv = "this strategy's table is not invertible (keys must be byte pairs, ids >= 256 and distinct)";
+    if (detok_state == 1) return BLT_OK;
+    if (detok_state < 0) return bltc::fail(detok_state, not_inv);
+    if (mode == bltc::Mode::BpeGeneral) {
+        detok_state = BLT_ERR_INVALID_INPUT;
+        return bltc::fail(detok_state, not_inv);
+    }
+    std::vector<uint16_t> dec(bltk::kPairTableEntries, 0);
+    std::vector<uint32_t> exists(2048, 0);
+    // later duplicates of a key overwrite (HashMap::insert, config_loader.rs:39): invert the FINAL map
+    std::vector<int32_t> final_id(65536, -1);
+    for (const auto &r : rules) final_id[size_t(r.left) | (size_t(r.right) << 8)] = int32_t(r.value);
+    uint32_t max_id = 255, count = 0;
+    for (uint32_t key = 0; key < 65536; ++key) {
+        if (final_id[key] < 0) continue;
+        const uint32_t id = uint32_t(final_id[key]);
+        if ((exists[id >> 5] >> (id & 31)) & 1u) {
+            detok_state = BLT_ERR_INVALID_INPUT;
+            return bltc::fail(detok_state, not_inv);
+        }
+        exists[id >> 5] |= 1u << (id & 31);
+        dec[id] = uint16_t(key);  // l | r << 8
+        max_id = std::max(max_id, id);
+        ++count;
+    }
+    detok_limit = max_id + 1;
+    detok_holes = (count != max_id - 255) ? 1u : 0u;
+    if (cudaSetDevice(ctx->device) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void **>(&d_detok), dec.size() * 2 + exists.size() * 4) != cudaSuccess)
+        return bltc::fail(BLT_ERR_NOMEM, "cudaMalloc failed for the detokenizer table");
+    if (cudaMemcpy(d_detok, dec.data(), dec.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(reinterpret_cast<unsigned char *>(d_detok) + dec.size() * 2, exists.data(), exists.size() * 4,
+                   cudaMemcpyHostToDevice) != cudaSuccess)
+        return bltc::fail(BLT_ERR_CUDA, "copying the detokenizer table failed");
+    detok_state = 1;
+    return BLT_OK;
 }
 
 namespace bltc {
@@ -274,6 +355,7 @@ blt_strategy::~blt_strategy() {
     if (d_slots) cudaFree(d_slots);
     if (d_can_left) cudaFree(d_can_left);
     if (d_can_right) cudaFree(d_can_right);
+    if (d_detok) cudaFree(d_detok);
     resident.release();
 }
 
@@ -381,6 +463,39 @@ int blt_process_resident(blt_strategy *s, const void *d_in, size_t n, size_t chu
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = run_device(s, s->resident, static_cast<const uint8_t *>(d_in), n, chunk_size, static_cast<uint8_t *>(d_out),
                         out_cap, d_chunk_ends, st, &s->resident_result);
+    if (rc) return rc;
+    if (out_len) {
+        rc = finish_result(s->resident, st, &s->resident_result);
+        if (rc) return rc;
+        if (s->resident_result.kind == DeviceResult::KNOWN) CUDA_TRY(cudaStreamSynchronize(st));
+        *out_len = s->resident_result.len;
+    }
+    return BLT_OK;
+}
+
+int blt_detokenize_host(blt_strategy *s, const uint8_t *in, size_t n_bytes, int has_content_type, uint8_t *out,
+                        size_t out_cap, size_t *out_len) {
+    if (!s || !out_len || (n_bytes && !in) || !out) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    *out_len = 0;
+    if (n_bytes & 1) return fail(BLT_ERR_INVALID_DATA, "token stream has an odd number of bytes");
+    if (has_content_type) {  // prepend_content_type_token's inverse (lib.rs:284-294)
+        if (n_bytes < 2) return fail(BLT_ERR_INVALID_DATA, "missing content-type token");
+        const uint32_t t = (uint32_t(in[0]) << 8) | in[1];
+        if (t < 0xFF01u || t > 0xFF04u) return fail(BLT_ERR_INVALID_DATA, "missing content-type token");
+        in += 2;
+        n_bytes -= 2;
+    }
+    return bltc::detokenize_host(s, in, n_bytes, out, out_cap, out_len);
+}
+
+int blt_detokenize_resident(blt_strategy *s, const void *d_tokens, size_t n_bytes, void *d_out, size_t out_cap,
+                            void *stream, size_t *out_len) {
+    if (!s || (n_bytes && (!d_tokens || !d_out))) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->resident_mu);
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = run_detok(s, s->resident, static_cast<const uint8_t *>(d_tokens), n_bytes, static_cast<uint8_t *>(d_out), out_cap,
+                       st, &s->resident_result);
     if (rc) return rc;
     if (out_len) {
         rc = finish_result(s->resident, st, &s->resident_result);

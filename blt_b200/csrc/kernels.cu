@@ -449,7 +449,11 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
 }
 
 
+#include "detok.cuh"
+
 }  // namespace
+
+cudaError_t launch_detokenize(const DetokArgs &a, cudaStream_t stream) { return launch_detok_impl(a, stream); }
 
 // ---- scratch -------------------------------------------------------------------------------------
 size_t sweep_scratch_bytes(size_t n_elems_max) {

@@ -73,6 +73,20 @@ struct SweepArgs {
     SweepScratch scratch;
 };
 
+// Detokenizer (detok.cuh): n_tok big-endian u16 tokens -> bytes.
+struct DetokArgs {
+    const uint16_t *in;      // device, 16-byte aligned
+    size_t n_tok;
+    uint8_t *out;            // device, 16-byte aligned
+    size_t out_cap;          // bytes
+    const uint16_t *table;   // device: 65536 x u16 (id -> l | r << 8), then 2048 x u32 "id exists" bitmap
+    uint32_t limit;          // ids >= limit do not exist
+    uint32_t holes;          // 1: ids below limit may be missing too (consult the bitmap)
+    SweepScratch scratch;    // total_tokens receives the output BYTES; ctrl word 6 = "unknown token seen"
+};
+cudaError_t launch_detokenize(const DetokArgs &a, cudaStream_t stream);
+constexpr int kLaunchesDetok = 3;
+
 // K1.  16-byte loads, 32-byte stores.  n bytes in -> 2n bytes out (00 b pairs).
 cudaError_t launch_widen(const uint8_t *d_in, size_t n, uint8_t *d_out, cudaStream_t stream);
 // chunk_ends[k] = bytes_per_elem * min((k+1)*chunk, n) for the fixed-ratio strategies.

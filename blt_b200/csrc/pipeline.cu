@@ -127,6 +127,7 @@ struct ChunkSource {
     size_t n = 0, chunk = 0;           // units of `chunk` bytes of an n-byte input
     size_t first = 0, count = 0, stride = 1;  // this pipeline owns units first, first+stride, ... (count of them)
     size_t wall = 0;                   // the reference's chunk size inside a unit (0: unit == chunk)
+    bool detok = false;                // units are token bytes to detokenize
     size_t id_of(size_t i) const { return first + i * stride; }
     size_t len_of(size_t id) const { return std::min(chunk, n - id * chunk); }
 };
@@ -145,7 +146,8 @@ int run_slots(blt_strategy *s, Pipe &pipe, const ChunkSource &src, Fetch fetch, 
         CUDA_TRY(cudaEventRecord(sl.ev_h2d, pipe.s_h2d));
         CUDA_TRY(cudaStreamWaitEvent(pipe.s_comp, sl.ev_h2d, 0));
         if (reuse) CUDA_TRY(cudaStreamWaitEvent(pipe.s_comp, sl.ev_d2h, 0));  // d_out free once copied out
-        int rc = run_device(s, pipe.ws, sl.d_in, sl.in_len, src.wall, sl.d_out, 2 * pipe.cap, nullptr, pipe.s_comp, &sl.res);
+        int rc = src.detok ? run_detok(s, pipe.ws, sl.d_in, sl.in_len, sl.d_out, 2 * pipe.cap, pipe.s_comp, &sl.res)
+                           : run_device(s, pipe.ws, sl.d_in, sl.in_len, src.wall, sl.d_out, 2 * pipe.cap, nullptr, pipe.s_comp, &sl.res);
         if (rc) return rc;
         if (sl.res.kind == DeviceResult::IN_SCRATCH)
             CUDA_TRY(cudaMemcpyAsync(sl.h_ctrl, pipe.ws.scratch.ctrl, 32, cudaMemcpyDeviceToHost, pipe.s_comp));
@@ -218,6 +220,48 @@ int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, in
             });
     }
     if (rc != BLT_OK) {  // drain whatever is in flight before the pipe is reused
+        cudaStreamSynchronize(pipe->s_h2d);
+        cudaStreamSynchronize(pipe->s_comp);
+        cudaStreamSynchronize(pipe->s_d2h);
+    }
+    s->ctx->give_back(std::move(pipe));
+    if (rc == BLT_OK) *out_len = off;
+    return rc;
+}
+
+// Host memory -> host memory detokenizer: units of 64 MiB of tokens through the same three-stream pipeline
+// (any token boundary is a valid cut: tokens expand independently).
+int detokenize_host(blt_strategy *s, const uint8_t *in, size_t n_bytes, uint8_t *out, size_t out_cap, size_t *out_len) {
+    *out_len = 0;
+    if (n_bytes == 0) return BLT_OK;
+    if (s->mode == Mode::Passthrough) {
+        if (out_cap < n_bytes) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+        std::memcpy(out, in, n_bytes);
+        *out_len = n_bytes;
+        return BLT_OK;
+    }
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    int rc = s->ensure_detok();
+    if (rc) return rc;
+    const size_t unit = std::min(n_bytes, size_t(64) << 20);
+    ChunkSource src;
+    src.n = n_bytes; src.chunk = unit; src.first = 0; src.count = (n_bytes + unit - 1) / unit; src.stride = 1;
+    src.detok = true;
+    size_t off = 0;
+    auto pipe = s->ctx->acquire();
+    rc = pipe->ensure(unit, std::min(kSlots, src.count), false);
+    if (rc == BLT_OK) {
+        rc = run_slots(
+            s, *pipe, src, [&](size_t k, Slot &) { return in + k * unit; },
+            [&](size_t, Slot &sl, size_t len) -> int {
+                if (off + len > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+                CUDA_TRY(cudaMemcpyAsync(out + off, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
+                CUDA_TRY(cudaEventRecord(sl.ev_d2h, pipe->s_d2h));
+                off += len;
+                return BLT_OK;
+            });
+    }
+    if (rc != BLT_OK) {
         cudaStreamSynchronize(pipe->s_h2d);
         cudaStreamSynchronize(pipe->s_comp);
         cudaStreamSynchronize(pipe->s_d2h);

@@ -37,10 +37,13 @@ struct DeviceResult {
     uint32_t sweeps = 0;  // productive + verifying sweeps actually launched
     int launches = 0;     // kernels enqueued by the host
     blt_strategy *owner = nullptr;  // set when the dense pass was attempted: decode_ctrl reports back to it
+    uint32_t len_scale = 2;         // bytes per unit of the device's total (2: tokens, 1: detokenizer bytes)
 };
 
 int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, size_t chunk, uint8_t *d_out,
                size_t out_cap, uint64_t *d_chunk_ends, cudaStream_t stream, DeviceResult *res);
+int run_detok(blt_strategy *s, Workspace &ws, const uint8_t *d_tokens, size_t n_bytes, uint8_t *d_out, size_t out_cap,
+              cudaStream_t stream, DeviceResult *res);
 int finish_result(Workspace &ws, cudaStream_t stream, DeviceResult *res);
 int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res);
 
@@ -69,6 +72,7 @@ struct Pipe {
 
 int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, int content_type, uint8_t *out,
                   size_t out_cap, size_t *out_len);
+int detokenize_host(blt_strategy *s, const uint8_t *in, size_t n_bytes, uint8_t *out, size_t out_cap, size_t *out_len);
 
 }  // namespace bltc
 
@@ -98,6 +102,11 @@ struct blt_strategy {
     bool dense_always = false;            // BLT_DENSE=always: attempt on every call (tests)
     bool want_dense();
     void dense_feedback(bool failed);
+    std::mutex detok_mu;                  // detokenizer table, built on first use
+    uint16_t *d_detok = nullptr;          //   65536 x u16 + 2048 x u32 (DetokArgs::table)
+    uint32_t detok_limit = 0, detok_holes = 0;
+    int detok_state = 0;                  //   0 not built, 1 ready, < 0 the error code it failed with
+    int ensure_detok();
     std::mutex resident_mu;
     bltc::Workspace resident;             // workspace of blt_process_resident
     bltc::DeviceResult resident_result;

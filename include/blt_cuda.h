@@ -120,6 +120,21 @@ BLT_API int blt_process_resident(blt_strategy *s, const void *d_in, size_t n, si
  * most recent blt_process_resident call made on this strategy by the calling thread. */
 BLT_API int blt_resident_result(blt_strategy *s, void *stream, size_t *out_len, uint32_t *sweeps);
 
+/* ---- detokenizer: big-endian u16 tokens -> bytes ------------------------------------
+ * The reference has no detokenizer; this is the consumer of its wire format (tokenizer.rs:88-91, optional
+ * content-type token first, lib.rs:284-294) and the round-trip check of the tokenizer.  Defined for basic,
+ * passthrough (a copy) and for BPE tables whose keys are byte pairs and whose ids are >= 256 and distinct
+ * (every merges.txt table, config_loader.rs:27-40): token < 256 -> that byte, id of (l, r) -> bytes l r.
+ * Errors: BLT_ERR_INVALID_INPUT if the table is not invertible; BLT_ERR_INVALID_DATA for an odd byte
+ * count, a missing content-type token or a token that is not in the table; BLT_ERR_CAPACITY.  The output
+ * is never longer than the input (out_cap >= n_bytes always suffices). */
+BLT_API int blt_detokenize_host(blt_strategy *s, const uint8_t *in, size_t n_bytes, int has_content_type,
+                                uint8_t *out, size_t out_cap, size_t *out_len);
+/* Device-resident form: d_tokens / d_out are 16-byte aligned device pointers, no content-type token.
+ * out_len == NULL: returns when the work is enqueued (blt_resident_result gives the length later). */
+BLT_API int blt_detokenize_resident(blt_strategy *s, const void *d_tokens, size_t n_bytes, void *d_out,
+                                    size_t out_cap, void *stream, size_t *out_len);
+
 /* ---- run_tokenizer: file to file ---------------------------------------------------------------- */
 
 /* CoreConfig (blt_core/src/lib.rs:110-130) as built by CoreConfig::new_from_cli (lib.rs:149-174),

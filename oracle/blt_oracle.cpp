@@ -427,6 +427,38 @@ uint16_t ora_content_type_token(int ct) {  // lib.rs:96-103
     }
 }
 
+// Inverse of tokenizer.rs:88-91 + lib.rs:284-294 (no reference counterpart; see the header).
+int ora_detokenize(const ora_merges *m, const uint8_t *in, size_t n_bytes, int has_content_type,
+                   uint8_t *out, size_t out_cap, size_t *out_len) {
+    *out_len = 0;
+    std::vector<int32_t> inverse(65536, -1);  // id -> left | right << 8
+    if (m) {
+        for (const auto &kv : m->map) {
+            const uint32_t l = kv.first >> 16, r = kv.first & 0xffffu;
+            if (l > 255 || r > 255 || kv.second < 256 || inverse[kv.second] >= 0) return ORA_INVALID_INPUT;
+            inverse[kv.second] = int32_t(l | (r << 8));
+        }
+    }
+    if (n_bytes & 1) return ORA_INVALID_DATA;
+    size_t i = 0;
+    if (has_content_type) {
+        if (n_bytes < 2) return ORA_INVALID_DATA;
+        const uint32_t t = (uint32_t(in[0]) << 8) | in[1];
+        if (t < 0xFF01 || t > 0xFF04) return ORA_INVALID_DATA;
+        i = 2;
+    }
+    std::vector<uint8_t> bytes;
+    bytes.reserve(n_bytes);
+    for (; i < n_bytes; i += 2) {
+        const uint32_t t = (uint32_t(in[i]) << 8) | in[i + 1];  // u16::from_be_bytes
+        if (t < 256) { bytes.push_back(uint8_t(t)); continue; }
+        if (inverse[t] < 0) return ORA_INVALID_DATA;
+        bytes.push_back(uint8_t(inverse[t] & 0xff));
+        bytes.push_back(uint8_t(inverse[t] >> 8));
+    }
+    return copy_out(bytes, out, out_cap, out_len);
+}
+
 int ora_run_buffer(int mode, const ora_merges *m, const uint8_t *in, size_t n, size_t chunk_size,
                    size_t threads, int content_type_token, uint8_t *out, size_t out_cap,
                    size_t *out_len) {

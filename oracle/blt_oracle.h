@@ -88,6 +88,16 @@ size_t ora_determine_thread_count(int has_override, size_t override_val, size_t 
 /* ContentType::get_token_value (blt_core/src/lib.rs:96-103): 0 text,1 audio,2 bin,3 video. */
 uint16_t ora_content_type_token(int content_type);
 
+/* Detokenizer: the inverse of the wire format (big-endian u16 tokens, tokenizer.rs:88-91; optional
+ * content-type token first, lib.rs:284-294).  THE REFERENCE HAS NO DETOKENIZER: this
+ * is the checker of the GPU detokenizer and of round trips, defined only for tables whose keys are byte
+ * pairs and whose ids are >= 256 and distinct (every merges.txt table, config_loader.rs:27-40).
+ * token < 256 -> that byte; token = id of (l, r) -> bytes l r.  Errors: ORA_INVALID_INPUT if the table
+ * is not invertible, ORA_INVALID_DATA for an odd byte count, a missing/unknown content-type token or a
+ * token that is not in the table. */
+int ora_detokenize(const ora_merges *m, const uint8_t *in, size_t n_bytes, int has_content_type,
+                   uint8_t *out, size_t out_cap, size_t *out_len);
+
 #ifdef __cplusplus
 }
 #endif

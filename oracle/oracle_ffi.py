@@ -65,6 +65,7 @@ def lib():
     L.ora_determine_thread_count.restype = C.c_size_t
     L.ora_content_type_token.argtypes = [C.c_int]
     L.ora_content_type_token.restype = C.c_uint16
+    L.ora_detokenize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, szp]
     _lib = L
     return L
 
@@ -151,6 +152,19 @@ def run_buffer(mode: str, data, chunk_size: int, threads: int = 1, merges: Optio
                               C.c_void_p(out.ctypes.data), out.size, C.byref(out_len))
     if rc != ORA_OK:
         raise OracleError(rc, "run_buffer failed")
+    return out[: out_len.value]
+
+
+def detokenize(tokens, merges: Optional[Merges] = None, has_content_type: bool = False):
+    """Inverse of the wire format (no reference counterpart, see blt_oracle.h).  Returns a numpy uint8 array."""
+    import numpy as np
+    p, n, keep = _buf(tokens)
+    out = np.empty(max(n, 1), dtype=np.uint8)
+    out_len = C.c_size_t()
+    rc = lib().ora_detokenize(merges._h if merges is not None else None, p, n, 1 if has_content_type else 0,
+                              C.c_void_p(out.ctypes.data), out.size, C.byref(out_len))
+    if rc != ORA_OK:
+        raise OracleError(rc, "detokenize failed")
     return out[: out_len.value]
 
 

@@ -119,3 +119,27 @@ def load_bpe_merges_text(text: str) -> Merges:
         merges[(a, b)] = vocab
         vocab += 1
     return merges
+
+
+def detokenize(stream: bytes, merges: Optional[Merges] = None, has_content_type: bool = False) -> bytes:
+    """Inverse of to_be(): token < 256 -> that byte, id of (l, r) -> bytes l r (no reference counterpart;
+    second restatement of oracle/blt_oracle.cpp::ora_detokenize)."""
+    inverse = {}
+    for (l, r), v in (merges or {}).items():
+        if l > 255 or r > 255 or v < 256 or v in inverse:
+            raise ValueError("table is not invertible")
+        inverse[v] = (l, r)
+    if len(stream) % 2:
+        raise ValueError("odd number of bytes")
+    toks = [int.from_bytes(stream[i:i + 2], "big") for i in range(0, len(stream), 2)]
+    if has_content_type:
+        if not toks or not 0xFF01 <= toks[0] <= 0xFF04:
+            raise ValueError("missing content-type token")
+        toks = toks[1:]
+    out = bytearray()
+    for t in toks:
+        if t < 256:
+            out.append(t)
+        else:
+            out.extend(inverse[t])   # KeyError: token not in the table
+    return bytes(out)

@@ -409,6 +409,94 @@ def test_resident_beyond_4gib(ctx, torch_mod, oracle):
         s.close()
 
 
+def _resident_detok(torch, strat, toks: np.ndarray):
+    d_in = torch.from_numpy(np.ascontiguousarray(toks)).cuda() if toks.size else torch.empty(16, dtype=torch.uint8, device="cuda")
+    d_out = torch.full((toks.size + 32,), 0xEE, dtype=torch.uint8, device="cuda")
+    n = strat.detokenize_resident(d_in.data_ptr(), toks.size, d_out.data_ptr(), toks.size, torch.cuda.current_stream().cuda_stream)
+    assert bool((d_out[toks.size:] == 0xEE).all()), "wrote past the capacity"
+    return d_out[:n].cpu().numpy()
+
+
+def test_detokenize_vs_oracle(ctx, nat, torch_mod, oracle):
+    """GPU detokenizer against the oracle's on arbitrary valid token streams, ragged sizes,
+    contiguous ids and ids with holes, device-resident and host entry points."""
+    rng = np.random.default_rng(11)
+    tables = {
+        "contiguous": {(int(k) & 255, int(k) >> 8): 256 + i for i, k in enumerate(rng.choice(65536, 3000, replace=False))},
+        "holes": {(97 + i % 5, 97 + i // 5): 300 + 37 * i for i in range(25)},
+        "top": {(1, 2): 65535, (3, 4): 256},
+    }
+    for name, pairs in tables.items():
+        # later duplicates of a key overwrite: keep the final map, and drop ids that collide
+        final = {}
+        for k, v in pairs.items():
+            final[k] = v
+        ids = np.array(sorted(set(final.values())), dtype=np.int64)
+        if len(ids) != len(final):
+            continue
+        om = oracle.Merges(final)
+        s = ctx.bpe_from_pairs(final)
+        for n_tok in (0, 1, 2, 7, 8, 9, 255, 256, 257, 4097, 65536, 100001, 1 * MiB + 3, 3 * MiB + 5):
+            for p_wide in (0.0, 0.5, 1.0):
+                wide = rng.random(n_tok) < p_wide
+                toks = np.where(wide, ids[rng.integers(0, len(ids), n_tok)], rng.integers(0, 256, n_tok)).astype(">u2")
+                stream = toks.view(np.uint8)
+                want = oracle.detokenize(stream, om)
+                assert np.array_equal(_resident_detok(torch_mod, s, stream), want), (name, n_tok, p_wide)
+            assert np.array_equal(s.detokenize_host(stream), want), (name, n_tok)
+        s.close()
+    b = ctx.basic()
+    raw = rng.integers(0, 256, 1 * MiB + 77).astype(np.uint8)
+    assert np.array_equal(b.detokenize_host(b.tokenize_host(raw, chunk_size=65536)), raw)
+    p = ctx.passthrough()
+    assert np.array_equal(p.detokenize_host(raw[: 2 * (raw.size // 2)]), raw[: 2 * (raw.size // 2)])
+
+
+def test_detokenize_errors_and_prefix(ctx, nat, torch_mod, oracle):
+    pairs = {(97, 98): 256, (98, 97): 300}
+    s = ctx.bpe_from_pairs(pairs)
+    ok = np.frombuffer(b"\xff\x01\x01\x00\x00c\x01\x2c", dtype=np.uint8)          # Text prefix, (a,b), c, (b,a)
+    assert bytes(s.detokenize_host(ok, has_content_type=True)) == b"abcba"
+    for bad in (b"\x00", b"\x01\x01", b"\x01\x00" * 5000 + b"\x01\x2b", b"\xff\x01\x00a"):  # odd, unknown ids (hole, 299), prefix unasked
+        with pytest.raises(nat.BltError) as e:
+            s.detokenize_host(np.frombuffer(bad, dtype=np.uint8))
+        assert e.value.code == -3, bad[:8]
+    with pytest.raises(nat.BltError) as e:
+        s.detokenize_host(np.frombuffer(b"\x00a", dtype=np.uint8), has_content_type=True)
+    assert e.value.code == -3
+    with pytest.raises(nat.BltError) as e:                                              # capacity
+        s.detokenize_host(np.frombuffer(b"\x01\x00" * 64, dtype=np.uint8), out=np.empty(100, dtype=np.uint8))
+    assert e.value.code == -7
+    s.close()
+    for not_invertible in ({(97, 98): 256, (98, 97): 256}, {(97, 98): 256, (256, 99): 257}, {(97, 97): 97}):
+        g = ctx.bpe_from_pairs(not_invertible)
+        with pytest.raises(nat.BltError) as e:
+            g.detokenize_host(np.frombuffer(b"\x00a", dtype=np.uint8))
+        assert e.value.code == -2
+        g.close()
+
+
+@pytest.mark.parametrize("cfg", [2, 3])
+def test_round_trip_one_gib(ctx, torch_mod, cfg):
+    """Size-independent property at BASELINE size: detokenize(tokenize(x)) == x for the whole GiB, on the
+    device (sparse table -> exact sweep, full table -> dense pass)."""
+    from blt_b200 import synth
+    torch = torch_mod
+    n, chunk = 1 << 30, 16 * MiB
+    data = synth.text(n, synth.SEED_CONFIG[cfg])
+    l, r = synth.merges_from_sample(data, 256 if cfg == 2 else 32768)
+    s = ctx.bpe_from_pairs({(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))})
+    d_in = torch.from_numpy(data).cuda()
+    d_tok = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    n_tok_bytes = s.process_resident(d_in.data_ptr(), n, chunk, d_tok.data_ptr(), 2 * n, 0, stream)
+    d_back = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    n_back = s.detokenize_resident(d_tok.data_ptr(), n_tok_bytes, d_back.data_ptr(), n, stream)
+    assert n_back == n
+    assert torch.equal(d_back[:n], d_in)
+    s.close()
+
+
 def test_cli_file_to_file_and_stdin(oracle, tmp_path):
     from blt_b200 import synth
     data = synth.text(5 * MiB + 321, 4242)

@@ -212,3 +212,55 @@ def test_file_to_file_matches_buffer(oracle, tmp_path):
     with pytest.raises(oracle.OracleError) as ei:
         oracle.run_files("basic", str(tmp_path / "nope"), str(tmp_path / "out.bin"), 4096, 1)
     assert ei.value.kind == oracle.ORA_NOT_FOUND
+
+
+# ---- detokenizer (no reference counterpart: the two restatements pin each other and the round trip) ----
+
+def test_detokenize_round_trip_on_reference_vectors(oracle):
+    """tokenize -> detokenize gives the input back on every BPE / basic vector the reference holds."""
+    for row in REF["bpe"]:
+        if "merges_file" in row:
+            pairs = pm.load_bpe_merges_text(row["merges_file"])
+        else:
+            pairs = merges_dict(row["merges"])
+        invertible = all(a < 256 and b < 256 and v >= 256 for (a, b), v in pairs.items()) and \
+            len(set(pairs.values())) == len(pairs)
+        data = row["input"].encode()
+        toks = oracle.process_chunk("bpe", data, oracle.Merges(pairs))
+        if invertible:
+            assert bytes(oracle.detokenize(toks, oracle.Merges(pairs))) == data, row["src"]
+            assert pm.detokenize(toks, pairs) == data
+        else:
+            with pytest.raises(oracle.OracleError) as e:
+                oracle.detokenize(toks, oracle.Merges(pairs))
+            assert e.value.kind == -2
+    for row in REF["basic"]:
+        data = row["input"].encode() if isinstance(row["input"], str) else bytes(row["input"])
+        assert bytes(oracle.detokenize(oracle.process_chunk("basic", data))) == data
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.tuples(st.integers(97, 101), st.integers(97, 101)), max_size=12, unique=True),
+       st.binary(max_size=300), st.integers(1, 64), st.booleans())
+def test_detokenize_oracle_equals_model(oracle, keys, data, chunk, with_ct):
+    data = bytes(97 + b % 6 for b in data)
+    pairs = {k: 300 + 7 * i for i, k in enumerate(keys)}              # non-contiguous ids on purpose
+    om = oracle.Merges(pairs)
+    toks = bytes(oracle.run_buffer("bpe", data, chunk, 2, om, content_type_token=0xFF01 if with_ct else None))
+    assert bytes(oracle.detokenize(toks, om, with_ct)) == data
+    assert pm.detokenize(toks, pairs, with_ct) == data
+
+
+def test_detokenize_errors(oracle):
+    om = oracle.Merges({(97, 98): 256})
+    for bad, kind in ((b"\x00", -3), (b"\x01\x01", -3), (b"\xff\x01\x00a", -3)):   # odd, unknown id, prefix when none expected
+        with pytest.raises(oracle.OracleError) as e:
+            oracle.detokenize(bad, om)
+        assert e.value.kind == kind
+    with pytest.raises(oracle.OracleError):
+        oracle.detokenize(b"\x00a", om, has_content_type=True)        # prefix expected, absent
+    assert bytes(oracle.detokenize(b"\xff\x03\x01\x00\x00c", om, has_content_type=True)) == b"abc"
+    for pairs in ({(97, 98): 256, (98, 97): 256}, {(300, 98): 400}, {(97, 98): 99}):
+        with pytest.raises(oracle.OracleError) as e:
+            oracle.detokenize(b"", oracle.Merges(pairs))
+        assert e.value.kind == -2
