@@ -55,10 +55,18 @@ __global__ void __launch_bounds__(kCtaThreads, 1) detok_count_kernel(const Detok
     DetokWalk wk;
     wk.init(a.n_tok, warp, (long long)gridDim.x * (kCtaThreads / 32));
     unsigned long long bytes = 0;
-    for (; wk.cur < wk.end; ++wk.cur) {
-        uint32_t nv;
-        const uint4 w = detok_load(a, wk.cur, lane, &nv);
-        bytes += nv + __popc(detok_wide_mask(w));  // absent tokens are zero: never wide
+    constexpr int RB = 8;  // independent 16-byte loads in flight per lane
+    for (; wk.cur < wk.end; wk.cur += RB) {
+        uint4 wq[RB];
+        uint32_t nvq[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            nvq[r] = 0;
+            wq[r] = make_uint4(0, 0, 0, 0);
+            if (wk.cur + r < wk.end) wq[r] = detok_load(a, wk.cur + r, lane, &nvq[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) bytes += nvq[r] + __popc(detok_wide_mask(wq[r]));  // absent tokens are zero: never wide
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(FULL, bytes, d);
@@ -131,9 +139,22 @@ __global__ void __launch_bounds__(kCtaThreads, 1) detok_emit_kernel(const DetokA
     uint32_t pend = uint32_t(base & 15ull);
     uint32_t head = pend;
     bool bad = false;
-    for (; wk.cur < wk.end; ++wk.cur) {
-        uint32_t nv;
-        const uint4 w = detok_load(a, wk.cur, lane, &nv);
+    uint32_t idmax = 0;    // packed running maximum of the ids seen by the all-merged fast path (checked at the end)
+    constexpr int RB = 4;  // rounds loaded together: four independent 16-byte loads in flight per lane
+    for (; wk.cur < wk.end; wk.cur += RB) {
+      uint4 wq[RB];
+      uint32_t nvq[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+          nvq[r] = 0;
+          wq[r] = make_uint4(0, 0, 0, 0);
+          if (wk.cur + r < wk.end) wq[r] = detok_load(a, wk.cur + r, lane, &nvq[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (wk.cur + r >= wk.end) break;
+        const uint4 w = wq[r];
+        const uint32_t nv = nvq[r];
         const uint32_t wide = detok_wide_mask(w);
         const uint32_t cnt = nv + __popc(wide);
         uint32_t incl = cnt;
@@ -143,25 +164,102 @@ __global__ void __launch_bounds__(kCtaThreads, 1) detok_emit_kernel(const DetokA
             if (lane >= d) incl += t;
         }
         const uint32_t total = __shfl_sync(FULL, incl, 31);
-        unsigned char *sp = stage + pend + (incl - cnt);
         const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+        bool direct = false;
+        if (pend == 0 && total == 512u) {
+            // ---- every token of the round is a merged id and the output is vector-aligned: 8 lookups, one
+            // 16-byte store per lane straight from registers (the steady state on a full table's output) ----
+            uint32_t o4[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (uint32_t(k) < nv) {
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t ids = __byte_perm(words[k], 0, 0x2301);               // both halves byte-swapped
+                idmax = __vmaxu2(idmax, ids);
+                const uint32_t e0 = *reinterpret_cast<const uint16_t *>(smem + ((ids << 1) & 0x1FFFEu));
+                const uint32_t e1 = *reinterpret_cast<const uint16_t *>(smem + ((ids >> 15) & 0x1FFFEu));
+                if (HOLES) {
+                    const uint32_t i0 = ids & 0xffffu, i1 = ids >> 16;
+                    bad = bad || (((exists[i0 >> 5] >> (i0 & 31)) & (exists[i1 >> 5] >> (i1 & 31)) & 1u) == 0u);
+                }
+                o4[k] = e0 | (e1 << 16);
+            }
+            stg_stream_v4(a.out + wpos + 16ull * lane, make_uint4(o4[0], o4[1], o4[2], o4[3]));
+            wpos += 512u;
+            continue;
+        }
+        if (__all_sync(FULL, nv == 8)) {
+            // ---- full round: the lane's bytes are packed in registers (a tree of shifts by the widths) ----
+            // (branch-free: the table is read for narrow tokens too and the result dropped)
+            uint32_t v[8], wd[8], badm = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
                 const uint32_t half = (words[k >> 1] >> (16 * (k & 1))) & 0xffffu;   // stored: hi | lo << 8
                 const uint32_t id = __byte_perm(half, 0, 0x4401);                    // the token
-                if ((wide >> k) & 1u) {
-                    const uint32_t e = dec[id];
-                    bad = bad || id >= a.limit || (HOLES && ((exists[id >> 5] >> (id & 31)) & 1u) == 0u);
-                    sp[0] = static_cast<unsigned char>(e);
-                    sp[1] = static_cast<unsigned char>(e >> 8);
-                    sp += 2;
-                } else {
-                    sp[0] = static_cast<unsigned char>(id);
-                    sp += 1;
+                const uint32_t is_wide = (wide >> k) & 1u;
+                const uint32_t e = dec[id];
+                wd[k] = 8u + 8u * is_wide;
+                v[k] = is_wide ? e : (half >> 8);
+                uint32_t unknown = (id >= a.limit) ? 1u : 0u;
+                if (HOLES) unknown |= ~(exists[id >> 5] >> (id & 31)) & 1u;
+                badm |= unknown & is_wide;
+            }
+            bad = bad || badm != 0u;
+            const uint32_t c01 = v[0] | (v[1] << wd[0]), c23 = v[2] | (v[3] << wd[2]);
+            const uint32_t c45 = v[4] | (v[5] << wd[4]), c67 = v[6] | (v[7] << wd[6]);
+            const uint32_t w01 = wd[0] + wd[1], w45 = wd[4] + wd[5];                 // 16..32 bits
+            // d0 = c01 | c23 << w01, d1 = c45 | c67 << w45 (64-bit each, as two words; clamped funnel shifts)
+            const uint32_t d0l = c01 | __funnelshift_lc(0u, c23, w01), d0h = __funnelshift_lc(c23, 0u, w01);
+            const uint32_t d1l = c45 | __funnelshift_lc(0u, c67, w45), d1h = __funnelshift_lc(c67, 0u, w45);
+            const uint32_t sh2 = w01 + wd[2] + wd[3] - 32u;                          // S = d0 | d1 << (32 + sh2), sh2 in 0..32
+            const uint32_t s0 = d0l, s1 = d0h | __funnelshift_lc(0u, d1l, sh2);
+            const uint32_t s2 = __funnelshift_lc(d1l, d1h, sh2), s3 = __funnelshift_lc(d1h, 0u, sh2);
+            if (pend == 0 && total == 256u) {
+                // every token of the round is a plain byte and the output is vector-aligned: straight out
+                direct = true;
+                *reinterpret_cast<uint2 *>(a.out + wpos + 8ull * lane) = make_uint2(s0, s1);
+                wpos += total;
+            } else {
+                // place the lane's cnt bytes at byte offset o of the staging line with 4-byte stores: shift by
+                // o & 3, take the previous lane's incomplete last word into my first one, store my complete words
+                const uint32_t o = pend + (incl - cnt);
+                const uint32_t sh = (o & 3u) * 8u;
+                uint32_t t0 = s0 << sh;
+                const uint32_t t1 = __funnelshift_l(s0, s1, sh), t2 = __funnelshift_l(s1, s2, sh);
+                const uint32_t t3 = __funnelshift_l(s2, s3, sh), t4 = __funnelshift_l(s3, 0u, sh);
+                const uint32_t cw = ((o + cnt) >> 2) - (o >> 2);                     // complete words: 2..4
+                const bool ragged_end = ((o + cnt) & 3u) != 0u;
+                const uint32_t my_tail = !ragged_end ? 0u : (cw == 2 ? t2 : cw == 3 ? t3 : t4);
+                uint32_t prev = __shfl_up_sync(FULL, my_tail, 1);
+                uint32_t *sw = reinterpret_cast<uint32_t *>(stage) + (o >> 2);
+                if (lane == 0) prev = sh ? (sw[0] & ((1u << sh) - 1u)) : 0u;          // left by the previous round
+                t0 |= prev;
+                sw[0] = t0;
+                sw[1] = t1;
+                if (cw > 2) sw[2] = t2;
+                if (cw > 3) sw[3] = t3;
+                if (lane == 31 && ragged_end) sw[cw] = my_tail;
+            }
+        } else {
+            // ---- the ragged last round of the stream: byte stores ----
+            unsigned char *sp = stage + pend + (incl - cnt);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (uint32_t(k) < nv) {
+                    const uint32_t half = (words[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                    const uint32_t id = __byte_perm(half, 0, 0x4401);
+                    if ((wide >> k) & 1u) {
+                        const uint32_t e = dec[id];
+                        bad = bad || id >= a.limit || (HOLES && ((exists[id >> 5] >> (id & 31)) & 1u) == 0u);
+                        sp[0] = static_cast<unsigned char>(e);
+                        sp[1] = static_cast<unsigned char>(e >> 8);
+                        sp += 2;
+                    } else {
+                        sp[0] = static_cast<unsigned char>(id);
+                        sp += 1;
+                    }
                 }
             }
         }
+        if (direct) continue;
         __syncwarp();
         // flush the whole 16-byte vectors, keep the leftover (< 16 bytes) at the front of the line
         const uint32_t have = pend + total;
@@ -186,9 +284,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) detok_emit_kernel(const DetokA
             pend = have;
         }
         __syncwarp();
+      }
     }
     // the tail of the range: bytes [head, pend) of a vector shared with the next warp's range
     for (uint32_t k = head + lane; k < pend; k += 32) a.out[wpos + k] = stage[k];
+    bad = bad || (idmax & 0xffffu) >= a.limit || (idmax >> 16) >= a.limit;
     if (__any_sync(FULL, bad) && lane == 0) reinterpret_cast<uint32_t *>(a.scratch.ctrl)[6] = 1u;  // "unknown token"
 }
 

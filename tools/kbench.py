@@ -67,6 +67,38 @@ def general_map(peak):
     ctx.close()
 
 
+def detok(peak, n, chunk, iters):
+    """Detokenizer on the token streams of configs 3 (every token a merged id) and 2 (mixed)."""
+    stream = torch.cuda.current_stream().cuda_stream
+    for cfg, rules in ((3, 32768), (2, 256)):
+        data = synth.text(n, synth.SEED_CONFIG[cfg])
+        l, r = synth.merges_from_sample(data, rules)
+        ctx = nat.Context(0)
+        strat = ctx.bpe_from_pairs({(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))})
+        d_in = torch.from_numpy(data).cuda()
+        d_tok = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+        nt = strat.process_resident(d_in.data_ptr(), n, chunk, d_tok.data_ptr(), 2 * n, 0, stream, sync=True)
+        d_back = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            got = strat.detokenize_resident(d_tok.data_ptr(), nt, d_back.data_ptr(), n, stream, sync=True)
+        assert got == n and torch.equal(d_back[:n], d_in)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in evs:
+            a.record()
+            strat.detokenize_resident(d_tok.data_ptr(), nt, d_back.data_ptr(), n, stream, sync=False)
+            b.record()
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in evs)
+        med = ms[len(ms) // 2]
+        alg = nt + n
+        print(json.dumps({"config": f"detokenize config {cfg} tokens", "token_bytes": nt, "out_bytes": n, "ms_median": round(med, 4),
+                          "ms_best": round(ms[0], 4), "output_GBps": round(n / med / 1e6, 1), "algorithmic_GBps": round(alg / med / 1e6, 1),
+                          "frac_of_measured_hbm": round(alg / med / 1e6 / peak, 4)}), flush=True)
+        strat.close()
+        ctx.close()
+        del d_in, d_tok, d_back
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bytes", type=int, default=1 << 30)
@@ -84,6 +116,9 @@ def main():
     for cfg in [int(c) for c in args.configs.split(",")]:
         if cfg == 6:
             general_map(peak)
+            continue
+        if cfg == 7:
+            detok(peak, n, chunk, args.iters)
             continue
         if cfg == 1:
             data = synth.random_bytes(n, synth.SEED_CONFIG[1])
