@@ -309,6 +309,9 @@ def run_ours(args):
             if rank == 0:
                 pcie["all_ranks_both_directions_each"] = round(world * 3 * n / (float(t.item()) * 1e-3) / 1e9, 2)
         e2e = {"value": round(world * n * e_steps / (e_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "pcie_probe_GBps": pcie,
+               "of_pcie_ceiling": None if not pcie else round(
+                   world * n * e_steps / (e_ms * 1e-3) / 1e9 /
+                   (pcie.get("all_ranks_both_directions_each") or pcie["both_directions_each"]), 3),
                "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(out_bytes), "steps": e_steps,
                "ms_per_step": round(e_ms / e_steps, 3)}
 

@@ -128,8 +128,10 @@ struct ChunkSource {
     size_t first = 0, count = 0, stride = 1;  // this pipeline owns units first, first+stride, ... (count of them)
     size_t wall = 0;                   // the reference's chunk size inside a unit (0: unit == chunk)
     bool detok = false;                // units are token bytes to detokenize
+    std::vector<std::pair<size_t, size_t>> units;  // optional explicit (offset, length) list instead of uniform units
     size_t id_of(size_t i) const { return first + i * stride; }
-    size_t len_of(size_t id) const { return std::min(chunk, n - id * chunk); }
+    size_t len_of(size_t id) const { return units.empty() ? std::min(chunk, n - id * chunk) : units[id].second; }
+    size_t off_of(size_t id) const { return units.empty() ? id * chunk : units[id].first; }
 };
 
 template <class Fetch, class Sink>
@@ -205,12 +207,33 @@ int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, in
     while (per_unit < 8 && chunk * (per_unit * 2) <= (size_t(64) << 20) && chunk * per_unit < n) per_unit *= 2;
     const size_t unit = chunk * per_unit;
     ChunkSource src;
-    src.n = n; src.chunk = unit; src.wall = chunk; src.first = 0; src.count = (n + unit - 1) / unit; src.stride = 1;
+    src.n = n; src.chunk = unit; src.wall = chunk; src.first = 0; src.stride = 1;
+    // Copies in and out run side by side, but a unit's output only exists once its whole input has arrived:
+    // the D2H stream starts one unit late and trails the H2D stream by one unit at the end.  Both exposed
+    // times shrink with the unit, so the schedule ramps up from a single chunk (chunk, 2, 4, ...), runs full
+    // units in the middle and ramps down again (..., 4, 2, chunk).
+    {
+        const size_t n_chunks = (n + chunk - 1) / chunk;
+        size_t ramp_chunks = 0;
+        for (size_t u = per_unit / 2; u >= 1; u /= 2) ramp_chunks += u;
+        const bool ramp = per_unit > 1 && n_chunks >= 4 * per_unit;
+        const size_t body_end = ramp ? n_chunks - ramp_chunks : n_chunks;
+        size_t c = 0;
+        auto push = [&](size_t k) {
+            const size_t o = c * chunk;
+            src.units.emplace_back(o, std::min(k * chunk, n - o));
+            c += k;
+        };
+        if (ramp) for (size_t u = 1; u < per_unit; u *= 2) push(u);
+        while (c < body_end) push(std::min(per_unit, body_end - c));
+        if (ramp) for (size_t u = per_unit / 2; u >= 1; u /= 2) push(u);
+    }
+    src.count = src.units.size();
     auto pipe = s->ctx->acquire();
     int rc = pipe->ensure(std::min(unit, n), std::min(kSlots, src.count), false);
     if (rc == BLT_OK) {
         rc = run_slots(
-            s, *pipe, src, [&](size_t k, Slot &) { return in + k * unit; },
+            s, *pipe, src, [&](size_t k, Slot &) { return in + src.off_of(k); },
             [&](size_t, Slot &sl, size_t len) -> int {
                 if (off + len > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
                 CUDA_TRY(cudaMemcpyAsync(out + off, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
