@@ -65,6 +65,7 @@ def lib():
     L.blt_detokenize_host.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, szp]
     L.blt_detokenize_resident.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, szp]
     L.blt_run_tokenizer.argtypes = [C.POINTER(CoreConfig)]
+    L.blt_run_detokenizer.argtypes = [C.POINTER(CoreConfig)]
     L.blt_load_bpe_merges.argtypes = [C.c_char_p, u16p, u16p, u16p, C.c_size_t, szp]
     L.blt_parse_chunk_size.argtypes = [C.c_char_p, szp]
     L.blt_effective_chunk_size.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint64]
@@ -139,6 +140,16 @@ def run_tokenizer(input: Optional[str], output: Optional[str], merges_file: Opti
                      chunk_size.encode() if chunk_size is not None else None,
                      0 if memcap is None else 1, memcap or 0, 1 if passthrough else 0, num_gpus)
     check(lib().blt_run_tokenizer(C.byref(cfg)))
+
+
+def run_detokenizer(input: Optional[str], output: Optional[str], merges_file: Optional[str] = None,
+                    content_type: int = CONTENT_NONE, passthrough: bool = False) -> None:
+    """File-to-file inverse of run_tokenizer (no reference counterpart)."""
+    cfg = CoreConfig(os.fsencode(input) if input is not None else None,
+                     os.fsencode(output) if output is not None else None,
+                     os.fsencode(merges_file) if merges_file is not None else None,
+                     content_type, 0, 0, None, 0, 0, 1 if passthrough else 0, 1)
+    check(lib().blt_run_detokenizer(C.byref(cfg)))
 
 
 # ---- device objects --------------------------------------------------------------------------------

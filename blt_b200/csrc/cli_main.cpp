@@ -22,6 +22,7 @@ const char *kHelp =
     "      --threads <NUM>       Override worker count (default: auto based on cores)\n"
     "      --memcap <PERCENT>    Max RAM usage fraction (e.g., 70 for 70%)\n"
     "      --chunksize <SIZE>    Min/Max chunk size (e.g. 4MB, 256KB).\n"
+    "      --detokenize          Inverse: INPUT holds tokens, OUTPUT receives the bytes (--type: a content-type token is present)\n"
     "      --gpus <NUM>          GPUs to shard chunks over (default: 1; every extra GPU costs ~1 s of CUDA start-up)\n"
     "  -h, --help                Print help\n"
     "  -V, --version             Print version\n";
@@ -59,7 +60,7 @@ const char *kind_name(int code) {
 int main(int argc, char **argv) {
     std::string input, output, merges, type, chunksize;
     bool has_input = false, has_output = false, has_merges = false, has_chunk = false, passthrough = false;
-    bool has_threads = false, has_memcap = false;
+    bool has_threads = false, has_memcap = false, detokenize = false;
     unsigned long long threads = 0, memcap = 0, gpus = 0;
     int content_type = BLT_CONTENT_NONE;
 
@@ -102,6 +103,7 @@ int main(int argc, char **argv) {
             if (!parse_unsigned(v.c_str(), 255, &memcap)) usage_error("invalid value '" + v + "' for '--memcap <PERCENT>'");
             has_memcap = true;
         } else if (a == "--chunksize") { chunksize = need("--chunksize <SIZE>"); has_chunk = true; }
+        else if (a == "--detokenize") { if (has_val) usage_error("unexpected value for '--detokenize'"); detokenize = true; }
         else if (a == "--gpus") {
             const std::string v = need("--gpus <NUM>");
             if (!parse_unsigned(v.c_str(), 1024, &gpus)) usage_error("invalid value '" + v + "' for '--gpus <NUM>'");
@@ -145,7 +147,7 @@ int main(int argc, char **argv) {
         for (unsigned long long g = 0; g < (gpus ? gpus : 1); ++g) vis += (g ? "," : "") + std::to_string(g);
         setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
     }
-    const int rc = blt_run_tokenizer(&cfg);
+    const int rc = detokenize ? blt_run_detokenizer(&cfg) : blt_run_tokenizer(&cfg);
     if (rc != BLT_OK) {  // main.rs:100-103
         std::fprintf(stderr, "Error running tokenizer: %s\n", blt_last_error());
         (void)kind_name;

@@ -828,3 +828,77 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     cleanup();
     return rc;
 }
+
+// ---- detokenizer, file to file ----------------------------------------------------------------------
+extern "C" int blt_run_detokenizer(const blt_core_config *cfg) {
+    if (!cfg) return fail(BLT_ERR_INVALID_INPUT, "NULL config");
+    blth::MergeList rules;
+    if (cfg->merges_file) {
+        const blth::Error e = blth::load_merges_file(cfg->merges_file, &rules);
+        if (e) return fail(BLT_ERR_INVALID_INPUT, "Failed to load BPE merges: " + e.msg);
+    }
+    // input: the whole token stream (mmap, or stdin read to the end)
+    std::vector<uint8_t> held;
+    const uint8_t *in = nullptr;
+    size_t n = 0;
+    int in_fd = -1;
+    void *map = nullptr;
+    if (cfg->input) {
+        in_fd = open(cfg->input, O_RDONLY);
+        if (in_fd < 0)
+            return fail(errno == ENOENT ? BLT_ERR_NOT_FOUND : BLT_ERR_IO,
+                        std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
+        struct stat st;
+        if (fstat(in_fd, &st) != 0) { close(in_fd); return fail(BLT_ERR_IO, "fstat failed"); }
+        n = size_t(st.st_size);
+        if (n) {
+            map = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, in_fd, 0);
+            if (map == MAP_FAILED) { close(in_fd); return fail(BLT_ERR_IO, std::string("mmap failed: ") + std::strerror(errno)); }
+            in = static_cast<const uint8_t *>(map);
+        }
+    } else {
+        uint8_t buf[1 << 16];
+        for (;;) {
+            const ssize_t r = read(0, buf, sizeof buf);
+            if (r < 0) { if (errno == EINTR) continue; return fail(BLT_ERR_IO, "read failed"); }
+            if (r == 0) break;
+            held.insert(held.end(), buf, buf + r);
+        }
+        in = held.data();
+        n = held.size();
+    }
+    auto close_in = [&] { if (map) munmap(map, n); if (in_fd >= 0) close(in_fd); };
+    OutFile of;
+    if (cfg->output) {
+        of.fd = open(cfg->output, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (of.fd < 0) {
+            const int e = errno;
+            close_in();
+            return fail(e == ENOENT ? BLT_ERR_NOT_FOUND : BLT_ERR_IO, std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")");
+        }
+        of.seekable = (lseek(of.fd, 0, SEEK_CUR) != (off_t)-1);
+    } else {
+        of.fd = 1;
+    }
+    blt_ctx *ctx = nullptr;
+    blt_strategy *st = nullptr;
+    int rc = blt_ctx_create(0, &ctx);
+    if (rc == BLT_OK) {
+        if (cfg->passthrough) rc = blt_strategy_passthrough(ctx, &st);
+        else if (cfg->merges_file) {
+            std::vector<uint16_t> l, r, v;
+            for (const auto &m : rules) { l.push_back(m.left); r.push_back(m.right); v.push_back(m.value); }
+            rc = blt_strategy_bpe_from_pairs(ctx, l.data(), r.data(), v.data(), l.size(), &st);
+        } else rc = blt_strategy_basic(ctx, &st);
+    }
+    std::vector<uint8_t> out(std::max<size_t>(n, 1));
+    size_t out_len = 0;
+    if (rc == BLT_OK) rc = blt_detokenize_host(st, in, n, cfg->content_type != BLT_CONTENT_NONE, out.data(), out.size(), &out_len);
+    if (rc == BLT_OK) rc = of.write_at(out.data(), out_len, 0);
+    const std::string err = rc != BLT_OK ? std::string(blt_last_error()) : std::string();
+    if (st) blt_strategy_destroy(st);
+    if (ctx) blt_ctx_destroy(ctx);
+    if (cfg->output) close(of.fd);
+    close_in();
+    return rc == BLT_OK ? BLT_OK : fail(rc, err);
+}

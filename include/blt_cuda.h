@@ -157,6 +157,10 @@ typedef struct blt_core_config {
  * the strategy, size chunks, open input (mmap) / output, write the content-type prefix, run the
  * chunk pipeline with chunks sharded contiguously over the GPUs, write results in chunk order. */
 BLT_API int blt_run_tokenizer(const blt_core_config *cfg);
+/* The inverse, file to file (no reference counterpart): `input` holds big-endian u16 tokens, `output`
+ * receives the bytes; merges_file / passthrough select the table as above; content_type != NONE means the
+ * stream starts with a content-type token, which is checked and dropped.  One GPU, whole file in memory. */
+BLT_API int blt_run_detokenizer(const blt_core_config *cfg);
 
 /* ---- host-only helpers (no device needed) --------------------------------------------------------- */
 

@@ -522,6 +522,14 @@ def test_cli_file_to_file_and_stdin(oracle, tmp_path):
     assert r.stdout == be([256, 32, 99, 32, 256])
     r = subprocess.run([BLT, "--chunksize", "1KB"], input=b"some data", capture_output=True)
     assert r.stdout == bytes(oracle.run_buffer("basic", b"some data", 1 << 20, 1))
+    # --detokenize (an addition): the CLI undoes its own output, file to file and over pipes
+    assert subprocess.run([BLT, "--detokenize", "-i", str(tmp_path / "o2.bin"), "-o", str(tmp_path / "back.bin"), "--merges",
+                           str(tmp_path / "m.txt"), "--type", "text"]).returncode == 0
+    assert (tmp_path / "back.bin").read_bytes() == data.tobytes()
+    r = subprocess.run([BLT, "--detokenize", "--merges", str(tmp_path / "ab.txt")], input=be([256, 32, 99, 32, 256]), capture_output=True)
+    assert r.returncode == 0 and r.stdout == b"ab c ab"
+    r = subprocess.run([BLT, "--detokenize", "--merges", str(tmp_path / "ab.txt")], input=be([300]), capture_output=True)
+    assert r.returncode == 1 and b"not in the table" in r.stderr
     # empty file -> empty output
     (tmp_path / "empty").write_bytes(b"")
     assert subprocess.run([BLT, "-i", str(tmp_path / "empty"), "-o", str(tmp_path / "o3.bin"), "--merges", str(tmp_path / "m.txt")]).returncode == 0
