@@ -137,8 +137,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->u16", "data": "synthetic",
-        "config": {"workload": f"BPE {args.merges} merges, {n >> 20} MiB synthetic English-like text, 16 MiB chunks",
-                   "note": "CPU path, each step = a bounded prefix of the workload"},
+        "config": {"workload": f"BPE {args.merges} merges (u16 vocab), {n >> 20} MiB synthetic English-like text per GPU, "
+                               f"16 MiB chunks, device-resident (BASELINE.json configs[2])",
+                   "note": "reference arm: the same workload on the host cores (restated CPU path, in memory), "
+                           "each step = a bounded prefix of it"},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
                          "sample": f"first {sample >> 20} MiB of the workload per step, in memory, {threads} threads"},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
