@@ -64,6 +64,9 @@ def lib():
     L.blt_resident_result.argtypes = [vp, vp, szp, C.POINTER(C.c_uint32)]
     L.blt_detokenize_host.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, szp]
     L.blt_detokenize_resident.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, szp]
+    L.blt_count_pairs_host.argtypes = [vp, vp, C.c_size_t, vp]
+    L.blt_count_pairs_resident.argtypes = [vp, vp, C.c_size_t, vp, vp]
+    L.blt_select_merges.argtypes = [vp, C.c_size_t, C.c_int, vp, vp, szp]
     L.blt_run_tokenizer.argtypes = [C.POINTER(CoreConfig)]
     L.blt_run_detokenizer.argtypes = [C.POINTER(CoreConfig)]
     L.blt_load_bpe_merges.argtypes = [C.c_char_p, u16p, u16p, u16p, C.c_size_t, szp]
@@ -150,6 +153,14 @@ def run_detokenizer(input: Optional[str], output: Optional[str], merges_file: Op
                      os.fsencode(merges_file) if merges_file is not None else None,
                      content_type, 0, 0, None, 0, 0, 1 if passthrough else 0, 1)
     check(lib().blt_run_detokenizer(C.byref(cfg)))
+
+
+def select_merges(counts: np.ndarray, k: int, pad_unobserved: bool = False):
+    c = np.ascontiguousarray(counts, dtype=np.uint64)
+    left, right = np.empty(max(k, 1), dtype=np.uint8), np.empty(max(k, 1), dtype=np.uint8)
+    n = C.c_size_t()
+    check(lib().blt_select_merges(c.ctypes.data, k, 1 if pad_unobserved else 0, left.ctypes.data, right.ctypes.data, C.byref(n)))
+    return left[: n.value], right[: n.value]
 
 
 # ---- device objects --------------------------------------------------------------------------------
@@ -271,6 +282,20 @@ class Context:
             l[i], r[i], v[i] = a, b, val
         h = C.c_void_p()
         return self._wrap(lib().blt_strategy_bpe_from_pairs(self._h, l, r, v, n, C.byref(h)), h)
+
+    def count_pairs(self, data) -> np.ndarray:
+        """Adjacent-byte-pair histogram on the GPU: counts[b0 << 8 | b1] (uint64, 65 536 entries)."""
+        a = _as_u8(data)
+        counts = np.zeros(65536, dtype=np.uint64)
+        check(lib().blt_count_pairs_host(self._h, a.ctypes.data, a.size, counts.ctypes.data))
+        return counts
+
+    def count_pairs_resident(self, d_in: int, n: int, d_counts: int, stream: int = 0) -> None:
+        check(lib().blt_count_pairs_resident(self._h, d_in, n, d_counts, stream or None))
+
+    def train_merges(self, data, k: int, pad_unobserved: bool = False):
+        """The k most frequent adjacent byte pairs of `data`, in merges.txt order (ids 256, 257, ...)."""
+        return select_merges(self.count_pairs(data), k, pad_unobserved)
 
     def close(self) -> None:
         if self._h:

@@ -506,6 +506,53 @@ int blt_detokenize_resident(blt_strategy *s, const void *d_tokens, size_t n_byte
     return BLT_OK;
 }
 
+int blt_count_pairs_resident(blt_ctx *ctx, const void *d_in, size_t n, uint64_t *d_counts, void *stream) {
+    if (!ctx || !d_counts || (n && !d_in)) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    if (reinterpret_cast<uintptr_t>(d_in) & 15u) return fail(BLT_ERR_INVALID_INPUT, "device buffers must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(bltk::launch_pair_hist(static_cast<const unsigned char *>(d_in), n, reinterpret_cast<unsigned long long *>(d_counts),
+                                    true, static_cast<cudaStream_t>(stream)));
+    return BLT_OK;
+}
+
+int blt_count_pairs_host(blt_ctx *ctx, const uint8_t *in, size_t n, uint64_t *counts) {
+    if (!ctx || !counts || (n && !in)) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t unit = size_t(256) << 20;  // pairs START inside a unit; one byte of the next unit rides along
+    unsigned char *d_buf = nullptr;
+    unsigned long long *d_counts = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_counts), 65536 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_buf), std::min(n, unit) + 16);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, 65536 * sizeof(unsigned long long), nullptr);
+    for (size_t off = 0; e == cudaSuccess && off < n; off += unit) {
+        const size_t len = std::min(unit + 1, n - off);
+        e = cudaMemcpy(d_buf, in + off, len, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = bltk::launch_pair_hist(d_buf, len, d_counts, false, nullptr);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(counts, d_counts, 65536 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (d_buf) cudaFree(d_buf);
+    cudaFree(d_counts);
+    if (e != cudaSuccess) return fail(BLT_ERR_CUDA, std::string("pair histogram failed: ") + cudaGetErrorString(e));
+    return BLT_OK;
+}
+
+int blt_select_merges(const uint64_t *counts, size_t k, int pad_unobserved, uint8_t *left, uint8_t *right, size_t *n_out) {
+    if (!counts || !n_out || (k && (!left || !right))) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
+    if (k > 65280) return fail(BLT_ERR_INVALID_INPUT, "at most 65280 rules fit the u16 id space (config_loader.rs:18,40)");
+    std::vector<uint32_t> keys;
+    for (uint32_t key = 0; key < 65536; ++key)
+        if (counts[key]) keys.push_back(key);
+    std::sort(keys.begin(), keys.end(), [&](uint32_t a, uint32_t b) { return counts[a] != counts[b] ? counts[a] > counts[b] : a < b; });
+    size_t w = 0;
+    for (size_t i = 0; i < keys.size() && w < k; ++i, ++w) { left[w] = uint8_t(keys[i] >> 8); right[w] = uint8_t(keys[i] & 0xff); }
+    if (pad_unobserved)
+        for (uint32_t key = 0; key < 65536 && w < k; ++key)
+            if (!counts[key]) { left[w] = uint8_t(key >> 8); right[w] = uint8_t(key & 0xff); ++w; }
+    *n_out = w;
+    return BLT_OK;
+}
+
 int blt_resident_result(blt_strategy *s, void *stream, size_t *out_len, uint32_t *sweeps) {
     if (!s) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
     std::lock_guard<std::mutex> lk(s->resident_mu);

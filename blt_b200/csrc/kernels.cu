@@ -450,8 +450,14 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
 
 
 #include "detok.cuh"
+#include "pairhist.cuh"
 
 }  // namespace
+
+cudaError_t launch_pair_hist(const unsigned char *d_in, size_t n, unsigned long long *d_counts, bool zero_first,
+                             cudaStream_t stream) {
+    return launch_pair_hist_impl(d_in, n, d_counts, zero_first, stream);
+}
 
 cudaError_t launch_detokenize(const DetokArgs &a, cudaStream_t stream) { return launch_detok_impl(a, stream); }
 

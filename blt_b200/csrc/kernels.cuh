@@ -87,6 +87,11 @@ struct DetokArgs {
 cudaError_t launch_detokenize(const DetokArgs &a, cudaStream_t stream);
 constexpr int kLaunchesDetok = 3;
 
+// Adjacent-byte-pair histogram (pairhist.cuh): d_counts[b0 << 8 | b1] += occurrences, 65 536 x u64
+// (zero_first: cleared by the launch; otherwise accumulated into).
+cudaError_t launch_pair_hist(const unsigned char *d_in, size_t n, unsigned long long *d_counts, bool zero_first,
+                             cudaStream_t stream);
+
 // K1.  16-byte loads, 32-byte stores.  n bytes in -> 2n bytes out (00 b pairs).
 cudaError_t launch_widen(const uint8_t *d_in, size_t n, uint8_t *d_out, cudaStream_t stream);
 // chunk_ends[k] = bytes_per_elem * min((k+1)*chunk, n) for the fixed-ratio strategies.

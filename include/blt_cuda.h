@@ -135,6 +135,19 @@ BLT_API int blt_detokenize_host(blt_strategy *s, const uint8_t *in, size_t n_byt
 BLT_API int blt_detokenize_resident(blt_strategy *s, const void *d_tokens, size_t n_bytes, void *d_out,
                                     size_t out_cap, void *stream, size_t *out_len);
 
+/* ---- merges "training": pair histogram -> merges.txt lines ---------------------------
+ * The reference only consumes merges files (config_loader.rs:14-46); its benchmark tables are "the k most
+ * frequent adjacent byte pairs" of a sample, which is this histogram: counts[b0 << 8 | b1] = number of i with
+ * in[i] = b0 and in[i+1] = b1 (65 536 entries). */
+BLT_API int blt_count_pairs_host(blt_ctx *ctx, const uint8_t *in, size_t n, uint64_t *counts);
+/* d_in: device pointer, 16-byte aligned; d_counts: device array of 65 536 uint64, overwritten. */
+BLT_API int blt_count_pairs_resident(blt_ctx *ctx, const void *d_in, size_t n, uint64_t *d_counts, void *stream);
+/* Host: the k most frequent pairs, most frequent first, ties by b0*256+b1 ascending; if fewer than k pairs
+ * occur and pad_unobserved != 0, never-observed pairs follow in ascending b0*256+b1.
+ * left/right receive *n_out <= k entries: line i of the merges.txt is "left[i] right[i]" (id 256 + i). */
+BLT_API int blt_select_merges(const uint64_t *counts, size_t k, int pad_unobserved, uint8_t *left, uint8_t *right,
+                              size_t *n_out);
+
 /* ---- run_tokenizer: file to file ---------------------------------------------------------------- */
 
 /* CoreConfig (blt_core/src/lib.rs:110-130) as built by CoreConfig::new_from_cli (lib.rs:149-174),

@@ -497,6 +497,38 @@ def test_round_trip_one_gib(ctx, torch_mod, cfg):
     s.close()
 
 
+def _pair_counts_numpy(data: np.ndarray) -> np.ndarray:
+    if data.size < 2:
+        return np.zeros(65536, dtype=np.uint64)
+    keys = (data[:-1].astype(np.uint32) << 8) | data[1:]
+    return np.bincount(keys, minlength=65536).astype(np.uint64)
+
+
+def test_pair_histogram_and_training(ctx, torch_mod):
+    """the GPU pair histogram against numpy, and the tables it yields against the workload
+    generator's CPU rule (most frequent first, ties by b0*256+b1, padded with unobserved pairs)."""
+    from blt_b200 import synth
+    rng = np.random.default_rng(5)
+    cases = [np.zeros(0, np.uint8), np.array([7], np.uint8), np.array([7, 9], np.uint8), rng.integers(0, 256, 17, dtype=np.uint8),
+             rng.integers(0, 256, 16 * 1024 * 3 + 1, dtype=np.uint8), rng.integers(0, 256, 1 * MiB + 3, dtype=np.uint8),
+             np.zeros(300000, np.uint8),                      # one pair 299 999 times: u16 counters must be flushed in time
+             np.tile(np.frombuffer(b"ab", np.uint8), 100001), synth.text(40 * MiB + 5, 77)]
+    for data in cases:
+        assert np.array_equal(ctx.count_pairs(data), _pair_counts_numpy(data)), data.size
+    # device-resident entry point
+    data = cases[-1]
+    d_in = torch_mod.from_numpy(data).cuda()
+    d_counts = torch_mod.full((65536,), 123, dtype=torch_mod.int64, device="cuda")
+    ctx.count_pairs_resident(d_in.data_ptr(), data.size, d_counts.data_ptr(), torch_mod.cuda.current_stream().cuda_stream)
+    assert np.array_equal(d_counts.cpu().numpy().astype(np.uint64), _pair_counts_numpy(data))
+    # training == the workload generator's rule on the same sample
+    sample = data[: 16 * MiB]
+    for k, pad in ((256, False), (32768, True)):
+        l, r = ctx.train_merges(sample, k, pad)
+        wl, wr = synth.merges_from_sample(sample, k)
+        assert np.array_equal(l, wl) and np.array_equal(r, wr), k
+
+
 def test_cli_file_to_file_and_stdin(oracle, tmp_path):
     from blt_b200 import synth
     data = synth.text(5 * MiB + 321, 4242)

@@ -197,3 +197,22 @@ def test_cli_flags_and_exit_codes(tmp_path):
     assert not out.exists()
     r = subprocess.run([BLT, "--passthrough", "-i", str(tmp_path / "missing")], capture_output=True)
     assert r.returncode == 1 and b"Error running tokenizer" in r.stderr
+
+
+def test_select_merges_host_rule():
+    """blt_select_merges (host only): most frequent first, ties by b0*256+b1 ascending, optional padding."""
+    import numpy as np
+    from blt_b200 import _native as nat
+    counts = np.zeros(65536, dtype=np.uint64)
+    counts[(101 << 8) | 32] = 50      # "e "
+    counts[(116 << 8) | 104] = 50     # "th"  (tie: 101*256+32 < 116*256+104)
+    counts[(0 << 8) | 1] = 7
+    counts[(255 << 8) | 255] = 900
+    l, r = nat.select_merges(counts, 3)
+    assert list(zip(l.tolist(), r.tolist())) == [(255, 255), (101, 32), (116, 104)]
+    l, r = nat.select_merges(counts, 10)                     # only 4 pairs occur
+    assert len(l) == 4 and (l[3], r[3]) == (0, 1)
+    l, r = nat.select_merges(counts, 7, pad_unobserved=True)  # padded with (0,0), (0,2), (0,3): (0,1) occurs
+    assert list(zip(l.tolist(), r.tolist()))[4:] == [(0, 0), (0, 2), (0, 3)]
+    with pytest.raises(nat.BltError):
+        nat.select_merges(counts, 65281)

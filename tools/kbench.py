@@ -99,6 +99,30 @@ def detok(peak, n, chunk, iters):
         del d_in, d_tok, d_back
 
 
+def pair_hist(peak, n, iters):
+    """Adjacent-byte-pair histogram on text and on uniform random bytes (every counter hot)."""
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = nat.Context(0)
+    for name, data in (("text", synth.text(n, synth.SEED_CONFIG[3])), ("random bytes", synth.random_bytes(n, synth.SEED_CONFIG[1]))):
+        d_in = torch.from_numpy(data).cuda()
+        d_counts = torch.zeros(65536, dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            ctx.count_pairs_resident(d_in.data_ptr(), n, d_counts.data_ptr(), stream)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in evs:
+            a.record()
+            ctx.count_pairs_resident(d_in.data_ptr(), n, d_counts.data_ptr(), stream)
+            b.record()
+        torch.cuda.synchronize()
+        assert int(d_counts.sum().item()) == n - 1
+        ms = sorted(a.elapsed_time(b) for a, b in evs)
+        med = ms[len(ms) // 2]
+        print(json.dumps({"config": f"pair histogram, {name}", "n": n, "ms_median": round(med, 4), "ms_best": round(ms[0], 4),
+                          "input_GBps": round(n / med / 1e6, 1), "frac_of_measured_hbm": round(n / med / 1e6 / peak, 4)}), flush=True)
+        del d_in
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bytes", type=int, default=1 << 30)
@@ -119,6 +143,9 @@ def main():
             continue
         if cfg == 7:
             detok(peak, n, chunk, args.iters)
+            continue
+        if cfg == 8:
+            pair_hist(peak, n, args.iters)
             continue
         if cfg == 1:
             data = synth.random_bytes(n, synth.SEED_CONFIG[1])
