@@ -8,9 +8,12 @@
 // where start[i-1], and copies it otherwise.  Inside a maximal run of m = 1 the starts are the
 // positions at even distance from the run's first position, so a 16-element segment acts on the
 // incoming carry (= "my first element was consumed by the previous segment") either as the
-// identity (m all ones) or as a constant (m has a zero).  Carries are resolved with ballots inside
-// a warp, a 32-entry table inside a tile and a single-pass decoupled look-back across tiles; the
-// same look-back word carries the running output count, so compaction needs no second pass.
+// identity (m all ones) or as a constant (m has a zero).
+//
+// Files: this one holds the streaming kernels (widen_kernel, dense_pairs_kernel), the two lookup front ends
+// and the launchers; sweep3.cuh the exact sweep (count / scan / emit, no inter-CTA waiting); detok.cuh the
+// detokenizer; pairhist.cuh the pair histogram.  Everything is compiled as relocatable device code because
+// the dense pass launches the exact sweep from the device when its speculation fails.
 #include "kernels.cuh"
 
 #include <algorithm>
