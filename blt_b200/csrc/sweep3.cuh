@@ -63,6 +63,24 @@ struct TileWalk {
 template <class FE, int R>
 __device__ __forceinline__ void load_tile3(const SweepArgs &a, unsigned long long tile_base, int lane, uint4 *w, uint32_t *nx) {
     using C = Sweep3Cfg<FE, R>;
+    if (tile_base + C::TILE_ELEMS + 1 <= a.n) {
+        // interior tile (all but the last one or two of a launch): one 64-bit address, constant offsets,
+        // no bounds checks; the look-ahead elements exist
+        const unsigned char *p = static_cast<const unsigned char *>(a.in) + (tile_base + uint32_t(lane * C::SEG)) * FE::ELEM;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            w[r] = ldg_stream_v4(p + r * 512);
+            nx[r] = 0;
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (FE::ELEM == 1) nx[r] = p[r * 512 + 16];
+                else nx[r] = __byte_perm(uint32_t(*reinterpret_cast<const uint16_t *>(p + r * 512 + 16)), 0, 0x4401);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const unsigned long long g = tile_base + uint32_t(r * C::ROUND_ELEMS + lane * C::SEG);
