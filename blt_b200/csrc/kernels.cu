@@ -444,8 +444,9 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
         if (threadIdx.x == 0) {
             reinterpret_cast<uint32_t *>(a.scratch.ctrl)[5] = 1u;
             __threadfence();
-            const bool ok = (variant == 1) ? tail_launch_sweep3<PairsFE, 8>(a, p, exact_grid)
-                                           : tail_launch_sweep3<PairsFE, 4>(a, p, exact_grid);
+            const bool ok = (variant == 1)   ? tail_launch_sweep3<PairsFE, 8>(a, p, exact_grid)
+                            : (variant == 2) ? tail_launch_sweep3<PairsFE, 4, true>(a, p, exact_grid)
+                                             : tail_launch_sweep3<PairsFE, 4>(a, p, exact_grid);
             if (!ok) *a.scratch.overflow = 2u;  // reported as a CUDA error by the host (never seen so far)
         }
     }
@@ -466,12 +467,12 @@ cudaError_t launch_detokenize(const DetokArgs &a, cudaStream_t stream) { return 
 
 // ---- scratch -------------------------------------------------------------------------------------
 size_t sweep_scratch_bytes(size_t n_elems_max) {
-    const size_t tiles = std::max<size_t>((n_elems_max + kMinTileElems - 1) / kMinTileElems + 1, 2 * 8192);
-    return kCtrlBytes + tiles * 8 + tiles * 4;
+    const size_t tiles = 2 * 8192;
+    return kCtrlBytes + tiles * 8 + tiles * 4 + n_elems_max / 16 + 64;
 }
 SweepScratch sweep_scratch_carve(void *mem, size_t n_elems_max) {
     SweepScratch s;
-    const size_t tiles = std::max<size_t>((n_elems_max + kMinTileElems - 1) / kMinTileElems + 1, 2 * 8192);
+    const size_t tiles = 2 * 8192;
     unsigned char *p = static_cast<unsigned char *>(mem);
     s.ctrl = p;
     s.total_tokens = reinterpret_cast<uint64_t *>(p);
@@ -480,7 +481,8 @@ SweepScratch sweep_scratch_carve(void *mem, size_t n_elems_max) {
     s.dense_abort = reinterpret_cast<uint32_t *>(p + 384);
     s.tile_status = reinterpret_cast<uint64_t *>(p + kCtrlBytes);
     s.tile_desc = reinterpret_cast<uint32_t *>(p + kCtrlBytes + tiles * 8);
-    s.bytes = kCtrlBytes + tiles * 8 + tiles * 4;
+    s.meta = p + kCtrlBytes + tiles * 8 + tiles * 4;
+    s.bytes = sweep_scratch_bytes(n_elems_max);
     s.max_tiles = tiles;
     return s;
 }
@@ -511,7 +513,7 @@ cudaError_t launch_fill_chunk_ends(uint64_t *d_ends, size_t n, size_t chunk, uns
     return cudaGetLastError();
 }
 
-static const char *kVariantNames[] = {"r4", "r8"};
+static const char *kVariantNames[] = {"r4", "r8", "walk"};
 int num_sweep_variants() { return int(sizeof(kVariantNames) / sizeof(kVariantNames[0])); }
 const char *sweep_variant_name(int v) { return (v >= 0 && v < num_sweep_variants()) ? kVariantNames[v] : "?"; }
 
@@ -537,6 +539,7 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, 
         // the exact kernels are launched from the device if the speculation fails: they must be configured too
         unsigned exact_grid = 0;
         if (variant == 1) { err = Sweep3Launch<PairsFE, 8>::configure(dev); exact_grid = Sweep3Launch<PairsFE, 8>::grid_for(a.n, dev); }
+        else if (variant == 2) { err = Sweep3Launch<PairsFE, 4, true>::configure(dev); exact_grid = Sweep3Launch<PairsFE, 4, true>::grid_for(a.n, dev); }
         else { err = Sweep3Launch<PairsFE, 4>::configure(dev); exact_grid = Sweep3Launch<PairsFE, 4>::grid_for(a.n, dev); }
         if (err != cudaSuccess) return err;
         if (a.scratch.max_tiles < size_t(2 * kMaxRanges)) return cudaErrorInvalidValue;
@@ -555,6 +558,7 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, 
     if (host_launches) *host_launches = kLaunchesExact;
     switch (variant) {
         case 1: return launch_sweep3<PairsFE, 8>(a, p, stream);
+        case 2: return launch_sweep3<PairsFE, 4, true>(a, p, stream);
         default: return launch_sweep3<PairsFE, 4>(a, p, stream);
     }
 }

@@ -52,6 +52,7 @@ struct SweepScratch {
     uint32_t *dense_abort;   // ctrl+384: set by the dense kernel when its speculation fails (own line)
     uint64_t *tile_status;   // ctrl+512: per warp range: [w] carry_in<<63 | tokens before; [8192+w] tokens of the range
     uint32_t *tile_desc;     // after tile_status: per warp range: carry function flags
+    uint8_t *meta;           // after tile_desc: n_elems_max / 16 + 64 bytes (SweepArgs::meta)
     size_t bytes;            // size of the whole region
     size_t max_tiles;
 };
@@ -70,6 +71,7 @@ struct SweepArgs {
     size_t out_base_tokens;  // the first token of this sweep lands at out[out_base_tokens]
     uint64_t *chunk_ends;    // optional device array: inclusive prefix of OUTPUT BYTES per chunk
     size_t chunk_ends_base;  // bytes added to every chunk_ends entry (output before this launch)
+    uint8_t *meta;           // optional (K2 walk variant): one byte per 16-byte segment written by count, read by emit
     SweepScratch scratch;
 };
 

@@ -197,6 +197,22 @@ __global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a
             const uint32_t st = start_bits(m, cin0);
             const uint32_t cnt = __popc(valid & ~((st << 1) | cin0));
             cnt0 += __reduce_add_sync(FULL, cnt);
+            if (FE::kMembershipInValue && a.meta != nullptr) {
+                // what the walk variant of emit needs to know about this segment before it looks anything up:
+                // bit 0 carry_in (if the range's carry_in were 0), bit 1 "carry_in IS the range's carry_in"
+                // (everything before it in the range is identity), bit 2 one token fewer if that carry_in is 1,
+                // bits 3-6 tokens emitted for carry_in as in bit 0, minus 8 (a full segment emits 8..16),
+                // bit 7 every pair of the segment is a rule (identity: it merges all the way at either parity)
+                uint32_t dep = 0, d1 = 0;
+                if (t_id) {  // warp-uniform, and false for good after the range's first non-identity segment
+                    dep = (l_nid == 0u) ? 1u : 0u;
+                    const uint32_t st1 = start_bits(m, 1u);
+                    d1 = (cnt - __popc(valid & ~((st1 << 1) | 1u))) & 1u;
+                }
+                const uint32_t c8 = cnt >= 8u ? cnt - 8u : 0u;
+                const uint32_t mbyte = cin0 | (dep << 1) | (d1 << 2) | (c8 << 3) | (m == ALL ? 0x80u : 0u);
+                if (simple) a.meta[tile_base / SEG + uint32_t(r * 32 + lane)] = static_cast<uint8_t>(mbyte);  // only read for such tiles
+            }
             if (nid) {
                 if (t_id) {  // the first non-identity segment of the range is the only one whose count sees the range's carry_in
                     const int f = __ffs(nid) - 1;
@@ -302,7 +318,27 @@ __global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a,
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <class FE, int R>
+// One position of the walk variant: if the scan stands here (standing != 0) the table entry of the pair is read
+// (it is the big-endian token to emit either way: the merged id, or the element itself when the pair is not a
+// rule), stored at sp, and the next position stands unless the pair was a rule.  No branches.
+__device__ __forceinline__ void walk_step(uint32_t &sp, uint32_t &standing, uint32_t entry_addr) {
+    asm volatile(
+        "{\n\t.reg .pred p, h;\n\t.reg .b16 t;\n\t.reg .b32 e;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "mov.b16 t, 0;\n\t"
+        "@p ld.shared.u16 t, [%2];\n\t"
+        "@p st.shared.u16 [%0], t;\n\t"
+        "@p add.u32 %0, %0, 2;\n\t"
+        "cvt.u32.u16 e, t;\n\t"
+        "and.b32 e, e, 255;\n\t"
+        "setp.ne.u32 h, e, 0;\n\t"
+        "selp.u32 %1, 0, 1, h;\n\t}"
+        : "+r"(sp), "+r"(standing)
+        : "r"(entry_addr)
+        : "memory");
+}
+
+template <class FE, int R, bool WALK = false>
 __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a, const typename FE::Params fp) {
     using C = Sweep3Cfg<FE, R>;
     constexpr int SEG = C::SEG;
@@ -320,6 +356,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
     if (tw.tile >= tw.end || warp >= kMaxRanges) return;
     const uint64_t rv = a.scratch.tile_status[warp];
     uint32_t carry = uint32_t(rv >> 63);
+    const uint32_t range_carry = carry;                      // the carry entering this warp's range
     unsigned long long rel = rv & ~R_CARRY;                  // tokens emitted before the next round (this launch)
     // Output streaming state.  stage[0 .. pend) holds tokens not yet written; stage[0] corresponds to
     // a.out[wpos] and wpos is a multiple of 8 tokens (16 bytes).  The first `head` slots of the very first
@@ -364,6 +401,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
         uint4 w[R];
         uint32_t nx[R];
         load_tile3<FE, R>(a, tile_base, lane, w, nx);
+        uint32_t mbq[R];
+        if constexpr (WALK) {
+            if (simple) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) mbq[r] = a.meta[tile_base / SEG + uint32_t(r * 32 + lane)];
+            }
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const uint32_t off = uint32_t(r * C::ROUND_ELEMS + lane * SEG);
@@ -371,6 +415,74 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
             uint32_t next = __shfl_down_sync(FULL, FE::first_elem(w[r]), 1);
             if (lane == 31) next = nx[r];
             const bool wall_here = end_wall && r == R - 1 && lane == 31;
+            if constexpr (WALK) {
+            if (simple) {
+                // ---- walk variant: the count kernel left carry_in and token count of every segment ----
+                const uint32_t mb = mbq[r];
+                const uint32_t cin = (mb & 2u) ? range_carry : (mb & 1u);
+                const uint32_t cnt = ((mb >> 3) & 15u) + 8u - (cin & (mb >> 2) & (mb >> 1) & 1u);
+                uint32_t total = uint32_t(C::ROUND_ELEMS / 2);
+                if (__all_sync(FULL, (mb & 0x80u) != 0u)) {
+                    // dense warp-round (every lane merges all the way at the carry's parity): 8 lookups, vector store
+                    uint32_t hv[HV];
+                    fe.lookup_vals(w[r], next, carry, hv);
+                    if (pend == 0) {
+                        if (wpos + C::ROUND_ELEMS / 2 <= a.out_cap_tokens)
+                            stg_stream_v4(a.out + wpos + size_t(lane) * (SEG / 2), make_uint4(hv[0], hv[1], hv[HV > 2 ? 2 : 0], hv[HV > 3 ? 3 : 0]));
+                        else if (lane == 0) *a.scratch.overflow = 1u;
+                        wpos += C::ROUND_ELEMS / 2;
+                    } else {
+                        uint16_t *d = stage + pend + lane * (SEG / 2);
+                        if ((pend & 1u) == 0) {
+#pragma unroll
+                            for (int k = 0; k < HV; ++k) reinterpret_cast<uint32_t *>(d)[k] = hv[k];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < HV; ++k) { d[2 * k] = uint16_t(hv[k]); d[2 * k + 1] = uint16_t(hv[k] >> 16); }
+                        }
+                        __syncwarp();
+                        flush(total);
+                    }
+                } else {
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    const uint32_t pos = incl - cnt;
+                    total = __shfl_sync(FULL, incl, 31);
+                    // the scan walks the lane's 16 positions; only where it stands is the table read
+                    uint32_t sp = uint32_t(__cvta_generic_to_shared(stage + pend + pos));
+                    const uint32_t tb = uint32_t(__cvta_generic_to_shared(fe.tbl));
+                    uint32_t standing = cin ^ 1u;
+                    const uint32_t wd[5] = {w[r].x, w[r].y, w[r].z, w[r].w, next};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t we = wd[k], wo = __funnelshift_r(wd[k], wd[k + 1], 8);   // pairs at 4k,4k+2 / 4k+1,4k+3
+                        const uint32_t ye = we ^ ((we >> 7) & 0x01FF01FFu), yo = wo ^ ((wo >> 7) & 0x01FF01FFu);
+                        walk_step(sp, standing, tb + ((ye << 1) & 0x1FFFEu));
+                        walk_step(sp, standing, tb + ((yo << 1) & 0x1FFFEu));
+                        walk_step(sp, standing, tb + ((ye >> 15) & 0x1FFFEu));
+                        if (k == 3 && wall_here) {  // the chunk's last element: never a pair, emitted as it is
+                            if (standing) {
+                                *reinterpret_cast<uint16_t *>(__cvta_shared_to_generic(sp)) = uint16_t(FE::raw_be(w[r], SEG - 1));
+                                sp += 2;
+                            }
+                            standing = 1u;
+                        } else {
+                            walk_step(sp, standing, tb + ((yo >> 15) & 0x1FFFEu));
+                        }
+                    }
+                    __syncwarp();
+                    flush(total);
+                    carry = __shfl_sync(FULL, standing ^ 1u, 31);
+                }
+                rel += total;
+                if (wall_here && a.chunk_ends != nullptr) a.chunk_ends[tw.ti.ck0] = a.chunk_ends_base + 2ull * rel;
+                continue;
+            }
+            }
             // ---- dense warp-round: the pairs of the carry's parity are all rules ----
             uint32_t hv[HV], ov[HV], valid;
             int have_par = -1;
@@ -463,7 +575,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
     }
 }
 
-template <class FE, int R>
+template <class FE, int R, bool WALK = false>
 struct Sweep3Launch {
     using C = Sweep3Cfg<FE, R>;
     static constexpr size_t smem_count = FE::TABLE_BYTES;
@@ -477,7 +589,7 @@ struct Sweep3Launch {
         if (!configured[dev].load(std::memory_order_acquire)) {
             cudaError_t err = cudaFuncSetAttribute(count_kernel<FE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_count));
             if (err != cudaSuccess) return err;
-            err = cudaFuncSetAttribute(emit_kernel<FE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_emit));
+            err = cudaFuncSetAttribute(emit_kernel<FE, R, WALK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_emit));
             if (err != cudaSuccess) return err;
             configured[dev].store(true, std::memory_order_release);
         }
@@ -495,9 +607,11 @@ struct Sweep3Launch {
 };
 
 // Host launch: control block cleared, then count, scan, emit on `stream`.
-template <class FE, int R>
-cudaError_t launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, cudaStream_t stream) {
-    using L = Sweep3Launch<FE, R>;
+template <class FE, int R, bool WALK = false>
+cudaError_t launch_sweep3(const SweepArgs &a_in, const typename FE::Params &fp, cudaStream_t stream) {
+    using L = Sweep3Launch<FE, R, WALK>;
+    SweepArgs a = a_in;
+    a.meta = WALK ? a.scratch.meta : nullptr;
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
@@ -509,18 +623,20 @@ cudaError_t launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, cud
     const unsigned grid = L::grid_for(a.n, dev);
     count_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_count, stream>>>(a, fp);
     scan_kernel<<<1, kCtaThreads, 0, stream>>>(a, int(grid * (kCtaThreads / 32)));
-    emit_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, stream>>>(a, fp);
+    emit_kernel<FE, R, WALK><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, stream>>>(a, fp);
     return cudaGetLastError();
 }
 
 // Device launch (CUDA dynamic parallelism, tail-launch stream): the same three kernels, enqueued by the dense
 // pass when its speculation failed.  They start when the launching grid has completed and run in order.
 // The caller has cleared the control block.  Returns false if a launch was refused.
-template <class FE, int R>
-__device__ bool tail_launch_sweep3(const SweepArgs &a, const typename FE::Params &fp, unsigned grid) {
-    using L = Sweep3Launch<FE, R>;
+template <class FE, int R, bool WALK = false>
+__device__ bool tail_launch_sweep3(const SweepArgs &a_in, const typename FE::Params &fp, unsigned grid) {
+    using L = Sweep3Launch<FE, R, WALK>;
+    SweepArgs a = a_in;
+    a.meta = WALK ? a.scratch.meta : nullptr;
     count_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_count, cudaStreamTailLaunch>>>(a, fp);
     scan_kernel<<<1, kCtaThreads, 0, cudaStreamTailLaunch>>>(a, int(grid * (kCtaThreads / 32)));
-    emit_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, cudaStreamTailLaunch>>>(a, fp);
+    emit_kernel<FE, R, WALK><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, cudaStreamTailLaunch>>>(a, fp);
     return cudaGetLastError() == cudaSuccess;
 }

@@ -119,7 +119,7 @@ def _random_case(rng, n, alphabet, density):
     return np.ascontiguousarray(data), pairs
 
 
-@pytest.mark.parametrize("variant,dense", [(0, "always"), (1, "always"), (0, "0"), (1, "0"), (0, "1")])
+@pytest.mark.parametrize("variant,dense", [(0, "always"), (1, "always"), (2, "always"), (0, "0"), (1, "0"), (2, "0"), (0, "1")])
 def test_random_vs_oracle_all_variants(nat, torch_mod, oracle, variant, dense, monkeypatch):
     """Both tile sizes of the exact sweep; the dense speculative pass attempted on every call (its failure
     launches the exact sweep from the device), never, or as the predictor decides (the default)."""
