@@ -41,17 +41,21 @@ int Pipe::ensure(size_t chunk_cap, size_t n_slots, bool want_pinned) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
     }
-    const bool regrow = chunk_cap > cap || (want_pinned && !pinned);
-    if (regrow) {
+    if (chunk_cap > cap) {
         for (Slot &sl : slots) {
             if (sl.d_in) cudaFree(sl.d_in);
             if (sl.d_out) cudaFree(sl.d_out);
+            sl.d_in = sl.d_out = nullptr;
+        }
+        cap = chunk_cap;
+    }
+    if (want_pinned && chunk_cap > pin_cap) {
+        for (Slot &sl : slots) {
             if (sl.h_in) cudaFreeHost(sl.h_in);
             if (sl.h_out) cudaFreeHost(sl.h_out);
-            sl.d_in = sl.d_out = sl.h_in = sl.h_out = nullptr;
+            sl.h_in = sl.h_out = nullptr;
         }
-        cap = std::max(chunk_cap, cap);
-        pinned = pinned || want_pinned;
+        pin_cap = chunk_cap;
     }
     if (slots.size() < n_slots) slots.resize(n_slots);
     for (size_t i = 0; i < n_slots; ++i) {
@@ -66,9 +70,9 @@ int Pipe::ensure(size_t chunk_cap, size_t n_slots, bool want_pinned) {
             CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_in), cap + 64));
             CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&sl.d_out), 2 * cap + 64));
         }
-        if (pinned && !sl.h_in) {
-            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_in), cap, cudaHostAllocDefault));
-            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_out), 2 * cap, cudaHostAllocDefault));
+        if (want_pinned && !sl.h_in) {
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_in), pin_cap, cudaHostAllocDefault));
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_out), 2 * pin_cap, cudaHostAllocDefault));
         }
     }
     return BLT_OK;
@@ -92,6 +96,7 @@ void Pipe::release() {
     s_h2d = s_comp = s_d2h = nullptr;
     ws.release();
     cap = 0;
+    pin_cap = 0;
 }
 
 }  // namespace bltc
@@ -116,6 +121,96 @@ void blt_ctx::give_back(std::unique_ptr<bltc::Pipe> p) {
 namespace bltc {
 
 namespace {
+
+// A blocking parallel-for over a few helper threads: the host-side copies of the file pipeline (page
+// cache -> pinned staging, pinned staging -> output file) are memory-bound single-threaded otherwise.
+// The reference spreads the same work over its tokio workers (`--threads`, utils.rs:79-97).
+class HostPool {
+  public:
+    explicit HostPool(size_t helpers) {
+        for (size_t i = 0; i < helpers; ++i) threads_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    size_t width() const { return threads_.size() + 1; }
+    // runs fn(0..parts-1); the caller takes part in the work; returns when every part is done
+    template <class F>
+    void run(size_t parts, F fn) {
+        if (parts <= 1 || threads_.empty()) { for (size_t i = 0; i < parts; ++i) fn(i); return; }
+        std::function<void(size_t)> f = fn;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &f; next_ = 0; parts_ = parts; pending_ = parts;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void work() {
+        for (;;) {
+            size_t i;
+            const std::function<void(size_t)> *f;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= parts_) return;
+                i = next_++;
+                f = fn_;
+            }
+            (*f)(i);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop() {
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || (fn_ && next_ < parts_); });
+                if (stop_) return;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t next_ = 0, parts_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
+
+
+// One process-wide pool for callers that hand in pageable buffers (blt_process_chunk from the reference's
+// workers): whoever finds it free copies with its helpers, everybody else copies alone.
+void shared_par_memcpy(uint8_t *dst, const uint8_t *src, size_t len) {
+    static HostPool pool(std::min<size_t>(8, std::max<size_t>(2, std::thread::hardware_concurrency() / 2)) - 1);
+    static std::mutex busy;
+    constexpr size_t kPiece = size_t(1) << 20;
+    if (len >= 4 * kPiece && busy.try_lock()) {
+        const size_t parts = std::min(pool.width(), (len + kPiece - 1) / kPiece);
+        const size_t per = ((len + parts - 1) / parts + 4095) & ~size_t(4095);
+        pool.run(parts, [&](size_t i) {
+            const size_t lo = i * per;
+            if (lo < len) std::memcpy(dst + lo, src + lo, std::min(per, len - lo));
+        });
+        busy.unlock();
+        return;
+    }
+    std::memcpy(dst, src, len);
+}
+
+bool is_pinned_host(const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
 
 // The slot-pipelined loop shared by the in-memory and the file pipelines.
 //   fetch(k, slot)      -> host pointer to chunk k's input bytes (may stage into slot.h_in)
@@ -203,8 +298,14 @@ int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, in
     // The pipeline moves UNITS of several reference chunks: one H2D, one launch (the kernels keep the
     // walls at multiples of `chunk`, which is exactly the concatenation of the per-chunk results) and one
     // D2H per unit.  Fewer, larger PCIe copies; the output bytes are the same.
+    // Pageable caller memory (the reference hands in slices of an mmap and takes a fresh Vec<u8>) would make
+    // every cudaMemcpyAsync a synchronous copy through the driver's own staging buffer (~3-5 GB/s, serialised
+    // across threads).  Such buffers are staged through the pipe's pinned slots with plain (parallel) memcpys.
+    const bool stage_in = !is_pinned_host(in), stage_out = !is_pinned_host(out);
+    const bool staged = stage_in || stage_out;
+    const size_t unit_limit = staged ? (size_t(16) << 20) : (size_t(64) << 20);
     size_t per_unit = 1;
-    while (per_unit < 8 && chunk * (per_unit * 2) <= (size_t(64) << 20) && chunk * per_unit < n) per_unit *= 2;
+    while (per_unit < 8 && chunk * (per_unit * 2) <= unit_limit && chunk * per_unit < n) per_unit *= 2;
     const size_t unit = chunk * per_unit;
     ChunkSource src;
     src.n = n; src.chunk = unit; src.wall = chunk; src.first = 0; src.stride = 1;
@@ -230,17 +331,39 @@ int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, in
     }
     src.count = src.units.size();
     auto pipe = s->ctx->acquire();
-    int rc = pipe->ensure(std::min(unit, n), std::min(kSlots, src.count), false);
+    int rc = pipe->ensure(std::min(unit, n), std::min(kSlots, src.count), staged);
+    // staged output is handed over one unit late, so that its D2H overlaps the next unit's staging
+    struct Pending { Slot *sl = nullptr; size_t len = 0, at = 0; } pend;
+    auto hand_over = [&](Pending &p) -> int {
+        if (!p.sl) return BLT_OK;
+        CUDA_TRY(cudaEventSynchronize(p.sl->ev_d2h));
+        shared_par_memcpy(out + p.at, p.sl->h_out, p.len);
+        p.sl = nullptr;
+        return BLT_OK;
+    };
     if (rc == BLT_OK) {
         rc = run_slots(
-            s, *pipe, src, [&](size_t k, Slot &) { return in + src.off_of(k); },
+            s, *pipe, src,
+            [&](size_t k, Slot &sl) -> const uint8_t * {
+                if (!stage_in) return in + src.off_of(k);
+                shared_par_memcpy(sl.h_in, in + src.off_of(k), src.len_of(k));
+                return sl.h_in;
+            },
             [&](size_t, Slot &sl, size_t len) -> int {
                 if (off + len > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
-                CUDA_TRY(cudaMemcpyAsync(out + off, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
+                if (stage_out) {
+                    int w = hand_over(pend);
+                    if (w) return w;
+                    CUDA_TRY(cudaMemcpyAsync(sl.h_out, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
+                    pend.sl = &sl; pend.len = len; pend.at = off;
+                } else {
+                    CUDA_TRY(cudaMemcpyAsync(out + off, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
+                }
                 CUDA_TRY(cudaEventRecord(sl.ev_d2h, pipe->s_d2h));
                 off += len;
                 return BLT_OK;
             });
+        if (rc == BLT_OK) rc = hand_over(pend);
     }
     if (rc != BLT_OK) {  // drain whatever is in flight before the pipe is reused
         cudaStreamSynchronize(pipe->s_h2d);
@@ -320,70 +443,6 @@ struct OutFile {
         }
         return BLT_OK;
     }
-};
-
-// A blocking parallel-for over a few helper threads: the host-side copies of the file pipeline (page
-// cache -> pinned staging, pinned staging -> output file) are memory-bound single-threaded otherwise.
-// The reference spreads the same work over its tokio workers (`--threads`, utils.rs:79-97).
-class HostPool {
-  public:
-    explicit HostPool(size_t helpers) {
-        for (size_t i = 0; i < helpers; ++i) threads_.emplace_back([this] { loop(); });
-    }
-    ~HostPool() {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
-        cv_.notify_all();
-        for (auto &t : threads_) t.join();
-    }
-    size_t width() const { return threads_.size() + 1; }
-    // runs fn(0..parts-1); the caller takes part in the work; returns when every part is done
-    template <class F>
-    void run(size_t parts, F fn) {
-        if (parts <= 1 || threads_.empty()) { for (size_t i = 0; i < parts; ++i) fn(i); return; }
-        std::function<void(size_t)> f = fn;
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            fn_ = &f; next_ = 0; parts_ = parts; pending_ = parts;
-        }
-        cv_.notify_all();
-        work();
-        std::unique_lock<std::mutex> lk(mu_);
-        done_.wait(lk, [this] { return pending_ == 0; });
-        fn_ = nullptr;
-    }
-
-  private:
-    void work() {
-        for (;;) {
-            size_t i;
-            const std::function<void(size_t)> *f;
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (!fn_ || next_ >= parts_) return;
-                i = next_++;
-                f = fn_;
-            }
-            (*f)(i);
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--pending_ == 0) done_.notify_all();
-        }
-    }
-    void loop() {
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [this] { return stop_ || (fn_ && next_ < parts_); });
-                if (stop_) return;
-            }
-            work();
-        }
-    }
-    std::vector<std::thread> threads_;
-    std::mutex mu_;
-    std::condition_variable cv_, done_;
-    const std::function<void(size_t)> *fn_ = nullptr;
-    size_t next_ = 0, parts_ = 0, pending_ = 0;
-    bool stop_ = false;
 };
 
 struct GpuShard {

@@ -63,10 +63,10 @@ struct Pipe {
     int device = 0;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     std::vector<Slot> slots;
-    size_t cap = 0;        // input bytes per slot
-    bool pinned = false;   // slots own pinned staging
+    size_t cap = 0;        // input bytes per slot (device buffers)
+    size_t pin_cap = 0;    // input bytes per slot of the pinned staging (0: none)
     Workspace ws;
-    int ensure(size_t chunk_cap, size_t n_slots, bool want_pinned);
+    int ensure(size_t chunk_cap, size_t n_slots, bool want_pinned);  // want_pinned: staging for chunk_cap bytes too
     void release();
 };
 
