@@ -273,6 +273,55 @@ int run_slots(blt_strategy *s, Pipe &pipe, const ChunkSource &src, Fetch fetch, 
     return BLT_OK;
 }
 
+// Runs the units of `src` through a leased pipe: host `in` -> device -> host `out` (appended from byte `off`).
+// stage_in / stage_out: that side is pageable and goes through the pipe's pinned slots.
+int run_host_units(blt_strategy *s, const ChunkSource &src, const uint8_t *in, uint8_t *out, size_t out_cap, size_t off,
+                   size_t unit_cap, bool stage_in, bool stage_out, size_t *out_len) {
+    auto pipe = s->ctx->acquire();
+    int rc = pipe->ensure(unit_cap, std::min(kSlots, src.count), stage_in || stage_out);
+    // staged output is handed over one unit late, so that its D2H overlaps the next unit's staging
+    struct Pending { Slot *sl = nullptr; size_t len = 0, at = 0; } pend;
+    auto hand_over = [&](Pending &p) -> int {
+        if (!p.sl) return BLT_OK;
+        CUDA_TRY(cudaEventSynchronize(p.sl->ev_d2h));
+        shared_par_memcpy(out + p.at, p.sl->h_out, p.len);
+        p.sl = nullptr;
+        return BLT_OK;
+    };
+    if (rc == BLT_OK) {
+        rc = run_slots(
+            s, *pipe, src,
+            [&](size_t k, Slot &sl) -> const uint8_t * {
+                if (!stage_in) return in + src.off_of(k);
+                shared_par_memcpy(sl.h_in, in + src.off_of(k), src.len_of(k));
+                return sl.h_in;
+            },
+            [&](size_t, Slot &sl, size_t len) -> int {
+                if (off + len > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+                if (stage_out) {
+                    int w = hand_over(pend);
+                    if (w) return w;
+                    CUDA_TRY(cudaMemcpyAsync(sl.h_out, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
+                    pend.sl = &sl; pend.len = len; pend.at = off;
+                } else {
+                    CUDA_TRY(cudaMemcpyAsync(out + off, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
+                }
+                CUDA_TRY(cudaEventRecord(sl.ev_d2h, pipe->s_d2h));
+                off += len;
+                return BLT_OK;
+            });
+        if (rc == BLT_OK) rc = hand_over(pend);
+    }
+    if (rc != BLT_OK) {  // drain whatever is in flight before the pipe is reused
+        cudaStreamSynchronize(pipe->s_h2d);
+        cudaStreamSynchronize(pipe->s_comp);
+        cudaStreamSynchronize(pipe->s_d2h);
+    }
+    s->ctx->give_back(std::move(pipe));
+    if (rc == BLT_OK) *out_len = off;
+    return rc;
+}
+
 }  // namespace
 
 int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, int content_type, uint8_t *out,
@@ -330,49 +379,7 @@ int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, in
         if (ramp) for (size_t u = per_unit / 2; u >= 1; u /= 2) push(u);
     }
     src.count = src.units.size();
-    auto pipe = s->ctx->acquire();
-    int rc = pipe->ensure(std::min(unit, n), std::min(kSlots, src.count), staged);
-    // staged output is handed over one unit late, so that its D2H overlaps the next unit's staging
-    struct Pending { Slot *sl = nullptr; size_t len = 0, at = 0; } pend;
-    auto hand_over = [&](Pending &p) -> int {
-        if (!p.sl) return BLT_OK;
-        CUDA_TRY(cudaEventSynchronize(p.sl->ev_d2h));
-        shared_par_memcpy(out + p.at, p.sl->h_out, p.len);
-        p.sl = nullptr;
-        return BLT_OK;
-    };
-    if (rc == BLT_OK) {
-        rc = run_slots(
-            s, *pipe, src,
-            [&](size_t k, Slot &sl) -> const uint8_t * {
-                if (!stage_in) return in + src.off_of(k);
-                shared_par_memcpy(sl.h_in, in + src.off_of(k), src.len_of(k));
-                return sl.h_in;
-            },
-            [&](size_t, Slot &sl, size_t len) -> int {
-                if (off + len > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
-                if (stage_out) {
-                    int w = hand_over(pend);
-                    if (w) return w;
-                    CUDA_TRY(cudaMemcpyAsync(sl.h_out, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
-                    pend.sl = &sl; pend.len = len; pend.at = off;
-                } else {
-                    CUDA_TRY(cudaMemcpyAsync(out + off, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
-                }
-                CUDA_TRY(cudaEventRecord(sl.ev_d2h, pipe->s_d2h));
-                off += len;
-                return BLT_OK;
-            });
-        if (rc == BLT_OK) rc = hand_over(pend);
-    }
-    if (rc != BLT_OK) {  // drain whatever is in flight before the pipe is reused
-        cudaStreamSynchronize(pipe->s_h2d);
-        cudaStreamSynchronize(pipe->s_comp);
-        cudaStreamSynchronize(pipe->s_d2h);
-    }
-    s->ctx->give_back(std::move(pipe));
-    if (rc == BLT_OK) *out_len = off;
-    return rc;
+    return run_host_units(s, src, in, out, out_cap, off, std::min(unit, n), stage_in, stage_out, out_len);
 }
 
 // Host memory -> host memory detokenizer: units of 64 MiB of tokens through the same three-stream pipeline
@@ -389,32 +396,12 @@ int detokenize_host(blt_strategy *s, const uint8_t *in, size_t n_bytes, uint8_t 
     CUDA_TRY(cudaSetDevice(s->ctx->device));
     int rc = s->ensure_detok();
     if (rc) return rc;
-    const size_t unit = std::min(n_bytes, size_t(64) << 20);
+    const bool stage_in = !is_pinned_host(in), stage_out = !is_pinned_host(out);
+    const size_t unit = std::min(n_bytes, (stage_in || stage_out) ? (size_t(16) << 20) : (size_t(64) << 20));
     ChunkSource src;
     src.n = n_bytes; src.chunk = unit; src.first = 0; src.count = (n_bytes + unit - 1) / unit; src.stride = 1;
     src.detok = true;
-    size_t off = 0;
-    auto pipe = s->ctx->acquire();
-    rc = pipe->ensure(unit, std::min(kSlots, src.count), false);
-    if (rc == BLT_OK) {
-        rc = run_slots(
-            s, *pipe, src, [&](size_t k, Slot &) { return in + k * unit; },
-            [&](size_t, Slot &sl, size_t len) -> int {
-                if (off + len > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
-                CUDA_TRY(cudaMemcpyAsync(out + off, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
-                CUDA_TRY(cudaEventRecord(sl.ev_d2h, pipe->s_d2h));
-                off += len;
-                return BLT_OK;
-            });
-    }
-    if (rc != BLT_OK) {
-        cudaStreamSynchronize(pipe->s_h2d);
-        cudaStreamSynchronize(pipe->s_comp);
-        cudaStreamSynchronize(pipe->s_d2h);
-    }
-    s->ctx->give_back(std::move(pipe));
-    if (rc == BLT_OK) *out_len = off;
-    return rc;
+    return run_host_units(s, src, in, out, out_cap, 0, unit, stage_in, stage_out, out_len);
 }
 
 // ====================================================================================================
