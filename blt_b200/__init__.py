@@ -73,6 +73,14 @@ class ByteTokenizer:
 
     def tokenize_file(self, input_path: str, output_path: str) -> None:
         """ByteTokenizer.tokenize_file (blt_python/src/lib.rs:98-165)."""
+        self._run(input_path, output_path, inverse=False)
+
+    def detokenize_file(self, input_path: str, output_path: str) -> None:
+        """The inverse of tokenize_file with the same merges / content_type (an addition: the reference has
+        no detokenizer): input_path holds the tokens, output_path receives the bytes."""
+        self._run(input_path, output_path, inverse=True)
+
+    def _run(self, input_path: str, output_path: str, inverse: bool) -> None:
         ct = {None: _native.CONTENT_NONE, "Text": _native.CONTENT_TEXT, "Bin": _native.CONTENT_BIN}[self.content_type]
         tmp = None
         try:
@@ -81,8 +89,11 @@ class ByteTokenizer:
                 with os.fdopen(fd, "w") as f:
                     f.write("".join(f"{a} {b}\n" for (a, b) in self.merges.keys()))
             try:
-                _native.run_tokenizer(input_path, output_path, tmp, ct, self.threads, self.chunk_size,
-                                      self.memory_cap, passthrough=False)
+                if inverse:
+                    _native.run_detokenizer(input_path, output_path, tmp, ct)
+                else:
+                    _native.run_tokenizer(input_path, output_path, tmp, ct, self.threads, self.chunk_size,
+                                          self.memory_cap, passthrough=False)
             except _native.BltError as e:
                 if e.code == _native.ERR_NOT_FOUND:
                     raise FileNotFoundError(e.message) from None

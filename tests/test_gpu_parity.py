@@ -585,5 +585,7 @@ def test_python_bytetokenizer(oracle, tmp_path):
     t = blt_b200.ByteTokenizer(threads=2, chunk_size="1MB", memory_cap=50, content_type="Bin")
     t.tokenize_file(str(tmp_path / "in.bin"), str(tmp_path / "out.bin"))
     assert (tmp_path / "out.bin").read_bytes() == b"\xff\x03" + bytes(oracle.run_buffer("basic", big, 1 << 20, 1))
+    t.detokenize_file(str(tmp_path / "out.bin"), str(tmp_path / "back.bin"))            # an addition: the inverse
+    assert (tmp_path / "back.bin").read_bytes() == big
     with pytest.raises(FileNotFoundError):
         blt_b200.ByteTokenizer().tokenize_file(str(tmp_path / "nope"), str(tmp_path / "out.bin"))
