@@ -317,8 +317,8 @@ __device__ __forceinline__ Walls<SEG> seg_walls(const SweepArgs &a, const TileIn
 // output is the looked-up id of every even pair, token k of the launch sits at out[k], and no carry
 // or count has to cross a tile.  With an even chunk size no such pair straddles a wall.  The kernel
 // streams under that hypothesis - 16 bytes in, 8 lookups, 16 bytes out per lane, no barrier, no
-// look-back - and raises `abort` at the first pair that is not a rule.  The exact sweep kernel is
-// always enqueued behind it and returns at once when the hypothesis held.
+// look-back - and raises `abort` at the first pair that is not a rule.  The last CTA to finish then either
+// publishes the totals or launches the exact sweep (sweep3.cuh) from the device, which redoes the launch.
 // ================================================================================================
 __global__ void __launch_bounds__(kCtaThreads, 1)
 dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int variant, unsigned exact_grid) {

@@ -352,9 +352,10 @@ int tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size_t chunk, in
     // across threads).  Such buffers are staged through the pipe's pinned slots with plain (parallel) memcpys.
     const bool stage_in = !is_pinned_host(in), stage_out = !is_pinned_host(out);
     const bool staged = stage_in || stage_out;
-    const size_t unit_limit = staged ? (size_t(16) << 20) : (size_t(64) << 20);
+    size_t unit_limit = staged ? (size_t(16) << 20) : (size_t(64) << 20);
+    if (const char *v = getenv("BLT_UNIT_MB")) unit_limit = size_t(std::max(1, atoi(v))) << 20;  // tuning knob
     size_t per_unit = 1;
-    while (per_unit < 8 && chunk * (per_unit * 2) <= unit_limit && chunk * per_unit < n) per_unit *= 2;
+    while (per_unit < 64 && chunk * (per_unit * 2) <= unit_limit && chunk * per_unit < n) per_unit *= 2;
     const size_t unit = chunk * per_unit;
     ChunkSource src;
     src.n = n; src.chunk = unit; src.wall = chunk; src.first = 0; src.stride = 1;
