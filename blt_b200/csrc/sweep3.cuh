@@ -135,6 +135,7 @@ __device__ __forceinline__ uint32_t segment_full(const FE &fe, const SweepArgs &
     } else {
         wl = seg_walls<SEG, TILE_ELEMS>(a, ti, off, g);
         valid = (g + SEG <= a.n) ? ALL : (g < a.n ? ((1u << uint32_t(a.n - g)) - 1) : 0u);
+        wl.endm &= valid;  // chunk walls behind the end of the input do not exist (they would index past chunk_ends)
     }
     if (wl.endm) {  // a wall suppresses the pair: the raw token is emitted there, not the merged id
 #pragma unroll

@@ -529,6 +529,52 @@ def test_pair_histogram_and_training(ctx, torch_mod):
         assert np.array_equal(l, wl) and np.array_equal(r, wr), k
 
 
+@pytest.mark.parametrize("variant,dense", [(0, "0"), (1, "0"), (2, "0"), (0, "always")])
+def test_no_writes_outside_the_buffers(nat, torch_mod, oracle, variant, dense, monkeypatch):
+    """Input, output (capacity exactly 2n) and chunk_ends (exactly one entry per chunk) sit between canaries
+    in one allocation: ragged sizes and tiny chunks must leave every canary and the input intact.  (Found by
+    tools/fuzz_gpu.py: chunk walls behind the end of the input used to write one entry past chunk_ends.)"""
+    torch = torch_mod
+    monkeypatch.setenv("BLT_SWEEP_VARIANT", str(variant))
+    monkeypatch.setenv("BLT_DENSE", dense)
+    c = nat.Context(0)
+    rng = np.random.default_rng(3)
+    pairs = {(97, 97): 256, (97, 98): 257, (98, 97): 258, (98, 98): 259, (99, 97): 260, (97, 99): 261, (99, 99): 262}
+    om = oracle.Merges(pairs)
+    s = c.bpe_from_pairs(pairs)
+    G = 4096
+    al = lambda x: (x + 255) // 256 * 256
+    stream = torch.cuda.current_stream().cuda_stream
+    for n, chunk in ((6, 0), (15, 0), (21, 0), (35, 16), (253, 2), (253, 16), (2119, 16), (4095, 2047), (4097, 4096),
+                     (2 * 4096 - 5, 4096), (70001, 1000), (1 * MiB + 9, 65536)):
+        data = rng.choice(np.array([97, 98, 99], dtype=np.uint8), size=n)
+        eff = chunk if chunk and chunk < n else n
+        nc = (n + eff - 1) // eff
+        want = oracle.run_buffer("bpe", data, eff, 2, om)
+        o_in = G; o_out = o_in + al(n) + G; o_ends = o_out + al(2 * n) + G; total = o_ends + al(8 * nc) + G
+        buf = torch.full((total,), 0xA5, dtype=torch.uint8, device="cuda")
+        buf[o_in:o_in + n] = torch.from_numpy(data).cuda()
+        base = buf.data_ptr()
+        for rep in range(2):
+            ln = s.process_resident(base + o_in, n, chunk, base + o_out, 2 * n, base + o_ends, stream)
+            h = buf.cpu().numpy()
+            assert np.array_equal(h[o_in:o_in + n], data), (n, chunk, rep, "input modified")
+            for lo, hi in ((0, o_in), (o_in + n, o_out), (o_out + 2 * n, o_ends), (o_ends + 8 * nc, total)):
+                assert np.all(h[lo:hi] == 0xA5), (n, chunk, rep, "canary", lo)
+            assert np.array_equal(h[o_out:o_out + ln], want), (n, chunk, rep)
+            assert int(h[o_ends:o_ends + 8 * nc].view(np.int64)[-1]) == want.size
+    s.close()
+    c.close()
+
+
+def test_fuzz_short():
+    """A bounded run of the randomised parity fuzzer (tools/fuzz_gpu.py) with a fixed seed."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_gpu.py"), "--seconds", "25", "--seed", "424242"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_cli_file_to_file_and_stdin(oracle, tmp_path):
     from blt_b200 import synth
     data = synth.text(5 * MiB + 321, 4242)
