@@ -56,16 +56,22 @@ while time.time() < t_end:
     want = ora.run_buffer("bpe", data, eff, 4, om)
     ok = True
     bad = []
-    # resident
-    d_in = torch.from_numpy(data).cuda() if n else torch.empty(16, dtype=torch.uint8, device="cuda")
-    d_out = torch.empty(2 * n + 16, dtype=torch.uint8, device="cuda")
+    # resident, inside canary-guarded buffers: output capacity exactly 2n, chunk_ends exactly one entry per chunk
+    G = 1024
+    al = lambda x: (x + 255) // 256 * 256
     nc = max(1, (n + eff - 1) // eff)
-    d_ends = torch.zeros(nc, dtype=torch.int64, device="cuda")
+    o_in = G; o_out = o_in + al(n) + G; o_ends = o_out + al(2 * n) + G; total = o_ends + al(8 * nc) + G
+    buf = torch.full((total,), 0xA5, dtype=torch.uint8, device="cuda")
+    if n: buf[o_in:o_in + n] = torch.from_numpy(data).cuda()
+    base = buf.data_ptr()
     for rep in range(rng.choice([1, 3])):
-        got_len = s.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), 2 * n, d_ends.data_ptr(), stream)
-        got = d_out[:got_len].cpu().numpy()
-        if not np.array_equal(got, want): bad.append(f"resident rep {rep}: len {got_len} vs {want.size}")
-        if n and int(d_ends[-1].item()) != want.size: bad.append(f"chunk_ends[-1] {int(d_ends[-1].item())} vs {want.size}")
+        got_len = s.process_resident(base + o_in, n, chunk, base + o_out, 2 * n, base + o_ends, stream)
+        h = buf.cpu().numpy()
+        if not np.array_equal(h[o_in:o_in + n], data): bad.append(f"resident rep {rep}: input modified")
+        for lo, hi in ((0, o_in), (o_in + n, o_out), (o_out + 2 * n, o_ends), (o_ends + 8 * nc, total)):
+            if not np.all(h[lo:hi] == 0xA5): bad.append(f"resident rep {rep}: canary at {lo} damaged")
+        if not np.array_equal(h[o_out:o_out + got_len], want): bad.append(f"resident rep {rep}: len {got_len} vs {want.size}")
+        if n and int(h[o_ends:o_ends + 8 * nc].view(np.int64)[-1]) != want.size: bad.append("chunk_ends[-1]")
     # host pipeline (pageable -> staged) and per-chunk call
     if not np.array_equal(s.tokenize_host(data, chunk_size=chunk or max(n, 1)), want): bad.append("tokenize_host")
     if n and n <= (1 << 20):
@@ -75,6 +81,25 @@ while time.time() < t_end:
         if not np.array_equal(s.detokenize_host(want), data): bad.append("detokenize round trip")
     except nat.BltError as e:
         bad.append(f"detokenize raised {e}")
+    # basic strategy and the pair histogram on the same bytes
+    b = ctx.basic()
+    if not np.array_equal(b.tokenize_host(data, chunk_size=chunk or max(n, 1)), ora.run_buffer("basic", data, eff, 2)): bad.append("basic")
+    b.close()
+    if n >= 2:
+        keys2 = (data[:-1].astype(np.uint32) << 8) | data[1:]
+        if not np.array_equal(ctx.count_pairs(data), np.bincount(keys2, minlength=65536).astype(np.uint64)): bad.append("pair histogram")
+    # a general map (second-level rules on produced ids): the multi-sweep hash path
+    if n <= 200000 and pairs:
+        gp = dict(pairs)
+        ids = list(pairs.values())
+        for i in range(min(8, len(ids))):
+            gp[(ids[i], rng.choice(syms))] = 60000 + i
+            gp[(rng.choice(syms), ids[-1 - i])] = 61000 + i
+        gm = ora.Merges(gp)
+        g = ctx.bpe_from_pairs(gp)
+        gw = ora.run_buffer("bpe", data, eff, 2, gm)
+        if not np.array_equal(g.tokenize_host(data, chunk_size=chunk or max(n, 1)), gw): bad.append("general map")
+        g.close()
     cases += 1
     ok = not bad
     if not ok:
