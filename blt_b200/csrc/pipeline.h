@@ -17,7 +17,7 @@ enum class Mode { Basic, Passthrough, BpePairs, BpeGeneral };
 
 int fail(int code, const std::string &msg);
 
-// Device scratch for one in-flight tokenization (look-back descriptors, multi-sweep ping-pong).
+// Device scratch for one in-flight tokenization (control block, range descriptors, multi-sweep ping-pong).
 struct Workspace {
     void *d_scratch = nullptr;
     size_t scratch_elems = 0;

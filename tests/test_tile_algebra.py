@@ -193,3 +193,96 @@ def test_dense_speculation_condition():
             if len(c) % 2:
                 got.append(c[-1])
         assert got == want
+
+
+def range_meta(ms, vms, seg):
+    """count_kernel with a.meta: per segment (cin0, dep, d1, cnt, ident) - sweep3.cuh, 'what the walk variant
+    of emit needs to know about this segment before it looks anything up'."""
+    t_id, t_const, meta = True, 0, []
+    for m, vm in zip(ms, vms):
+        ident, const = seg_fn(m, seg)
+        cin0 = 0 if t_id else t_const
+        c, _, _ = seg_count(m, vm, cin0, seg)
+        dep, d1 = 0, 0
+        if t_id:
+            dep = 1
+            c1, _, _ = seg_count(m, vm, 1, seg)
+            d1 = (c - c1) & 1
+        meta.append(dict(cin0=cin0, dep=dep, d1=d1, cnt=c, ident=ident))
+        if not ident:
+            t_id, t_const = False, const
+    return meta
+
+
+def emit_range_walk(meta, seg, range_carry, tokens, table, base_pos):
+    """emit_kernel<..., WALK>: carry_in and token count of every segment come from the meta byte; the lane then
+    walks its positions and reads the table only where the scan stands (walk_step)."""
+    out, carry = [], range_carry
+    for i, mb in enumerate(meta):
+        cin = range_carry if mb["dep"] else mb["cin0"]
+        cnt = mb["cnt"] - (cin & mb["d1"] & mb["dep"])
+        assert cin == carry, "the meta byte's carry_in is the carry the previous segment left"
+        k0 = base_pos + i * seg
+        if mb["ident"]:  # dense: every pair is a rule, merges all the way at the carry's parity
+            seg_out = [table[(tokens[k0 + j], tokens[k0 + j + 1])] for j in range(cin, seg, 2)]
+            standing_after = 1 - cin if seg % 2 == 0 else cin
+        else:
+            seg_out, standing = [], 1 - cin
+            for j in range(seg):
+                if standing:
+                    pair = (tokens[k0 + j], tokens[k0 + j + 1])
+                    hit = pair in table
+                    seg_out.append(table[pair] if hit else tokens[k0 + j])
+                    standing = 0 if hit else 1
+                else:
+                    standing = 1
+            standing_after = standing
+        assert len(seg_out) == cnt, (mb, cin, seg_out)
+        out += seg_out
+        carry = 1 - standing_after
+    return out, carry
+
+
+@pytest.mark.parametrize("seg,segs_per_range", [(4, 3), (16, 2), (8, 4)])
+def test_walk_variant_meta_and_walk(seg, segs_per_range):
+    """BLT_SWEEP_VARIANT=2 on wall-free, whole tiles (the only ones it handles itself): meta byte + walk equal
+    the sequential sweep; the identity bit - not the token count - is what marks a dense segment."""
+    rng = random.Random(seg * 77 + segs_per_range)
+    saw_cnt_half_not_ident = 0
+    for trial in range(400):
+        alpha = [97, 98, 99][: rng.choice([1, 2, 3])]
+        merges = {}
+        dens = rng.choice([0.4, 0.8, 1.0, 1.0])
+        for a in alpha:
+            for b in alpha:
+                if rng.random() < dens:
+                    merges[(a, b)] = 256 + len(merges)
+        r_elems = seg * segs_per_range
+        n_ranges = rng.randrange(1, 6)
+        n = n_ranges * r_elems
+        tokens = [rng.choice(alpha) for _ in range(n)]
+        if rng.random() < 0.4:
+            tokens = [alpha[0]] * n
+            if rng.random() < 0.6:
+                tokens[rng.randrange(0, min(n, 9))] = 120
+        want = pm.bpe_sweep(tokens, merges)[0]
+        padded = tokens + [0] * (seg + 1)          # the look-ahead element of the last segment (never a rule)
+        m_all = [1 if (i + 1 < n and (tokens[i], tokens[i + 1]) in merges) else 0 for i in range(n)]
+        out, carry = [], 0
+        prefix = dict(id=True, cst=0, delta=0, cnt0=0)
+        for t in range(n_ranges):
+            ms = [sum(m_all[t * r_elems + s * seg + j] << j for j in range(seg)) for s in range(segs_per_range)]
+            vms = [(1 << seg) - 1] * segs_per_range
+            fn, meta = range_function(ms, vms, seg), range_meta(ms, vms, seg)
+            for m, mb in zip(ms, meta):
+                if mb["cnt"] == seg // 2 and not mb["ident"]:
+                    saw_cnt_half_not_ident += 1
+            c_in = 0 if prefix["id"] else prefix["cst"]
+            assert c_in == carry
+            toks, carry = emit_range_walk(meta, seg, carry, padded, merges, t * r_elems)
+            out += toks
+            prefix = scan_compose(prefix, fn)
+        # the last element of the input has no partner: the kernel never takes that tile through the walk (it is
+        # not 'simple'); here the padded look-ahead 0 is simply not a rule
+        assert out == want, (tokens, merges)
+    assert saw_cnt_half_not_ident > 0  # seg/2 tokens without being all-rules happens: why the identity bit exists
