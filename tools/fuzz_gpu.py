@@ -81,6 +81,22 @@ while time.time() < t_end:
         if not np.array_equal(s.detokenize_host(want), data): bad.append("detokenize round trip")
     except nat.BltError as e:
         bad.append(f"detokenize raised {e}")
+    # detokenizer on an arbitrary valid token stream (not a tokenizer output), capacity exactly the answer's size
+    if pairs:
+        idsv = np.array(sorted(set(pairs.values())), dtype=np.int64)
+        nt = rng.choice([0, 1, 7, 255, 256, 257, rng.randint(0, 200000)])
+        wide = nrng.random(nt) < rng.choice([0.0, 0.3, 1.0])
+        toks = np.where(wide, idsv[nrng.integers(0, len(idsv), nt)], nrng.integers(0, 256, nt)).astype(">u2").view(np.uint8)
+        if len(set(pairs.values())) == len(pairs):
+            dw = ora.detokenize(toks, om)
+            o_t = G; o_b = o_t + al(toks.size) + G; tot2 = o_b + al(dw.size) + G
+            b2 = torch.full((tot2,), 0x5A, dtype=torch.uint8, device="cuda")
+            if toks.size: b2[o_t:o_t + toks.size] = torch.from_numpy(np.ascontiguousarray(toks)).cuda()
+            ln = s.detokenize_resident(b2.data_ptr() + o_t, toks.size, b2.data_ptr() + o_b, dw.size, stream)
+            h2 = b2.cpu().numpy()
+            if ln != dw.size or not np.array_equal(h2[o_b:o_b + ln], dw): bad.append("detokenize_resident")
+            for lo, hi in ((0, o_t), (o_t + toks.size, o_b), (o_b + dw.size, tot2)):
+                if not np.all(h2[lo:hi] == 0x5A): bad.append(f"detokenize canary at {lo}")
     # basic strategy and the pair histogram on the same bytes
     b = ctx.basic()
     if not np.array_equal(b.tokenize_host(data, chunk_size=chunk or max(n, 1)), ora.run_buffer("basic", data, eff, 2)): bad.append("basic")
