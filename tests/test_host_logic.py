@@ -216,3 +216,40 @@ def test_select_merges_host_rule():
     assert list(zip(l.tolist(), r.tolist()))[4:] == [(0, 0), (0, 2), (0, 3)]
     with pytest.raises(nat.BltError):
         nat.select_merges(counts, 65281)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/blt_cuda.h must compile as C (the boundary is a C ABI: cgo / Rust FFI / ctypes bind to it) and a
+    C program must link against libblt_cuda.so and use the host-only entry points."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "blt_b200", "lib")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include "blt_cuda.h"
+#include <stdio.h>
+#include <string.h>
+int main(void) {
+    size_t v = 0;
+    if (blt_parse_chunk_size("16MB", &v) != BLT_OK || v != 16u * 1024u * 1024u) return 1;
+    if (blt_parse_chunk_size("1gb", &v) != BLT_ERR_INVALID_INPUT) return 2;
+    if (blt_content_type_token(BLT_CONTENT_TEXT) != 0xFF01) return 3;
+    if (blt_effective_chunk_size(1, 1, 4, 80, 0) != 256u * 1024u) return 4;   /* clamp up, chunking.rs:29 */
+    if (strlen(blt_version()) == 0) return 5;
+    blt_core_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.chunk_size = "bogus";
+    if (blt_run_tokenizer(&cfg) != BLT_ERR_INVALID_INPUT) return 6;          /* config errors come before any device use */
+    printf("ok %s\n", blt_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lblt_cuda", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), (r.returncode, r.stdout, r.stderr)
