@@ -90,7 +90,8 @@ BLT_API size_t blt_strategy_num_merges(const blt_strategy *s);
 /* TokenizationStrategy::process_chunk(&self, &[u8]) -> io::Result<Vec<u8>> (tokenizer.rs:30;
  * called from pipeline.rs:144 and :343).  HOST buffers: `in` is borrowed for the call, the caller
  * owns `out`; out_cap >= 2*n always suffices.  n == 0 -> *out_len = 0 without a launch
- * (tokenizer.rs:57-59).  Re-entrant on one strategy. */
+ * (tokenizer.rs:57-59).  Re-entrant on one strategy.  Buffers may be ordinary pageable memory (they are
+ * staged through pinned buffers inside) or page-locked (cudaHostAlloc / cudaHostRegister: copied directly). */
 BLT_API int blt_process_chunk(blt_strategy *s, const uint8_t *in, size_t n, uint8_t *out,
                               size_t out_cap, size_t *out_len);
 
