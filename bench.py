@@ -272,7 +272,7 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        e_steps = max(1, min(args.steps, 5))
+        e_steps = max(1, min(args.steps, 20))
         got = 0
         for _ in range(2):
             got = strat.tokenize_host_ptr(h_in.data_ptr(), n, chunk, h_out.data_ptr(), h_out.numel())
