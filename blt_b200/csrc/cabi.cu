@@ -185,6 +185,7 @@ int finish_result(Workspace &ws, cudaStream_t stream, DeviceResult *res) {
 int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res) {
     const uint32_t overflow = reinterpret_cast<const uint32_t *>(h_ctrl)[4];
     if (overflow == 2u) return fail(BLT_ERR_CUDA, "device-side launch of the exact sweep was refused");
+    if (overflow == 3u) return fail(BLT_ERR_CUDA, "the fused sweep timed out waiting for a tile (look-back or bulk copy)");
     if (overflow) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
     if (res->owner) {  // the dense pass was attempted: tell the predictor how it went
         res->owner->dense_feedback(reinterpret_cast<const uint32_t *>(h_ctrl)[5] != 0u);

@@ -74,6 +74,19 @@ __device__ __forceinline__ uint4 widen8(uint32_t lo, uint32_t hi) {
     return r;
 }
 
+// V8: one 32-byte store per 16 input bytes (needs a 32-byte aligned output); otherwise two 16-byte stores (the
+// C ABI only promises 16-byte alignment, e.g. a slice of a larger device buffer).
+template <bool V8>
+__device__ __forceinline__ void widen_store(uint8_t *p, const uint4 &a) {
+    if (V8) {
+        stg_v8(p, widen8(a.x, a.y), widen8(a.z, a.w));
+    } else {
+        stg_stream_v4(p, widen8(a.x, a.y));
+        stg_stream_v4(p + 16, widen8(a.z, a.w));
+    }
+}
+
+template <bool V8>
 __global__ void __launch_bounds__(256) widen_kernel(const uint8_t *__restrict__ in, size_t n,
                                                     uint8_t *__restrict__ out) {
     const size_t nvec = n / 16;
@@ -83,12 +96,12 @@ __global__ void __launch_bounds__(256) widen_kernel(const uint8_t *__restrict__ 
     for (; i + stride < nvec; i += 2 * stride) {
         const uint4 a = ldg_stream_v4(in + i * 16);
         const uint4 b = ldg_stream_v4(in + (i + stride) * 16);
-        stg_v8(out + i * 32, widen8(a.x, a.y), widen8(a.z, a.w));
-        stg_v8(out + (i + stride) * 32, widen8(b.x, b.y), widen8(b.z, b.w));
+        widen_store<V8>(out + i * 32, a);
+        widen_store<V8>(out + (i + stride) * 32, b);
     }
     if (i < nvec) {
         const uint4 a = ldg_stream_v4(in + i * 16);
-        stg_v8(out + i * 32, widen8(a.x, a.y), widen8(a.z, a.w));
+        widen_store<V8>(out + i * 32, a);
     }
     // ragged tail (< 16 bytes), one thread
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -308,6 +321,7 @@ __device__ __forceinline__ Walls<SEG> seg_walls(const SweepArgs &a, const TileIn
 }
 
 #include "sweep3.cuh"
+#include "fused.cuh"
 
 // ================================================================================================
 // K2-dense: the speculative streaming form of the sweep for merge-dense input.
@@ -482,6 +496,7 @@ SweepScratch sweep_scratch_carve(void *mem, size_t n_elems_max) {
     s.tile_status = reinterpret_cast<uint64_t *>(p + kCtrlBytes);
     s.tile_desc = reinterpret_cast<uint32_t *>(p + kCtrlBytes + tiles * 8);
     s.meta = p + kCtrlBytes + tiles * 8 + tiles * 4;
+    s.meta_bytes = n_elems_max / 16 + 64;
     s.bytes = sweep_scratch_bytes(n_elems_max);
     s.max_tiles = tiles;
     return s;
@@ -499,7 +514,8 @@ cudaError_t launch_widen(const uint8_t *d_in, size_t n, uint8_t *d_out, cudaStre
     const size_t cap = size_t(sms) * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
-    widen_kernel<<<dim3(unsigned(blocks)), dim3(256), 0, stream>>>(d_in, n, d_out);
+    if ((reinterpret_cast<uintptr_t>(d_out) & 31u) == 0) widen_kernel<true><<<dim3(unsigned(blocks)), dim3(256), 0, stream>>>(d_in, n, d_out);
+    else widen_kernel<false><<<dim3(unsigned(blocks)), dim3(256), 0, stream>>>(d_in, n, d_out);
     return cudaGetLastError();
 }
 
@@ -513,7 +529,7 @@ cudaError_t launch_fill_chunk_ends(uint64_t *d_ends, size_t n, size_t chunk, uns
     return cudaGetLastError();
 }
 
-static const char *kVariantNames[] = {"r4", "r8", "walk"};
+static const char *kVariantNames[] = {"r4", "r8", "walk", "fused r8", "fused r4"};
 int num_sweep_variants() { return int(sizeof(kVariantNames) / sizeof(kVariantNames[0])); }
 const char *sweep_variant_name(int v) { return (v >= 0 && v < num_sweep_variants()) ? kVariantNames[v] : "?"; }
 
@@ -554,6 +570,14 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, 
                                                                                                   exact_grid);
         if (host_launches) *host_launches = kLaunchesDenseAttempt;
         return cudaGetLastError();
+    }
+    if (variant == 3 && FusedLaunch<2, 8, 8>::applicable(a)) {
+        if (host_launches) *host_launches = kLaunchesFused;
+        return FusedLaunch<2, 8, 8>::launch(a, d_table, stream);
+    }
+    if (variant == 4 && FusedLaunch<2, 8, 4>::applicable(a)) {
+        if (host_launches) *host_launches = kLaunchesFused;
+        return FusedLaunch<2, 8, 4>::launch(a, d_table, stream);
     }
     if (host_launches) *host_launches = kLaunchesExact;
     switch (variant) {

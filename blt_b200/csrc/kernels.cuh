@@ -52,7 +52,8 @@ struct SweepScratch {
     uint32_t *dense_abort;   // ctrl+384: set by the dense kernel when its speculation fails (own line)
     uint64_t *tile_status;   // ctrl+512: per warp range: [w] carry_in<<63 | tokens before; [8192+w] tokens of the range
     uint32_t *tile_desc;     // after tile_status: per warp range: carry function flags
-    uint8_t *meta;           // after tile_desc: n_elems_max / 16 + 64 bytes (SweepArgs::meta)
+    uint8_t *meta;           // after tile_desc: n_elems_max / 16 + 64 bytes (SweepArgs::meta; the fused sweep's tile descriptors)
+    size_t meta_bytes;
     size_t bytes;            // size of the whole region
     size_t max_tiles;
 };
@@ -109,7 +110,7 @@ cudaError_t launch_bpe_sweep_hash(const SweepArgs &a, const HashTableView &t, bo
                                   cudaStream_t stream);
 // Kernels the HOST enqueues per K2 call: the dense pass alone when it is attempted (it launches count, scan
 // and emit itself, from the device, only if its speculation fails); count + scan + emit otherwise.
-constexpr int kLaunchesDenseAttempt = 1, kLaunchesExact = 3;
+constexpr int kLaunchesDenseAttempt = 1, kLaunchesExact = 3, kLaunchesFused = 2;
 
 int num_sweep_variants();
 const char *sweep_variant_name(int variant);

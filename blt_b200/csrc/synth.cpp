@@ -94,6 +94,81 @@ void fill_period(uint8_t *out, size_t len, const char *pat) {
     for (size_t i = 0; i < len; ++i) out[i] = uint8_t(pat[i % p]);
 }
 
+// ---- mixed corpus (round 2): what a crawl or an archive looks like to a byte-level tokenizer ---------------
+// Segments of five kinds follow each other inside independent 1 MiB blocks (30 % English-like text from the lexicon
+// above, 12 % code/markup, 8 % UTF-8 script, 10 % base64, 40 % binary):
+// code/markup is ~90 printable ASCII symbols (Zipf 0.7), the script text is lead D0/D1 + continuation bytes,
+// base64 blobs are 64 uniform symbols and binary data uniform bytes.  All 256 byte values and all
+// 65 536 pairs occur, so a 32 768-rule table trained on it is a STRICT subset of the observed pairs: the sweep
+// meets non-rule pairs all the time (T_out / N_in ~ 0.57) and the carry / compaction machinery really runs.
+void mixed_block(uint8_t *out, size_t len, uint64_t seed, uint64_t block) {
+    const Lexicon &lx = lexicon();
+    static const char code_syms[] = " etaoinsrhldcumfpgwybvkxjqz(){};=.,_\"'<>/-+*&|![]:#0123456789ETAOINSRHLDCUMFPGWYBVKXJQZ\t\n@$%^~?`\\";
+    constexpr int n_code = int(sizeof code_syms) - 1;
+    static uint64_t code_cum[n_code];
+    static uint64_t code_total = [] {
+        uint64_t acc = 0;
+        for (int i = 0; i < n_code; ++i) {
+            // Zipf with exponent 0.7: weight ~ 1 / (i+1)^0.7, in integers
+            double w = 1.0;
+            for (int k = 0; k < 7; ++k) w *= double(i + 1);
+            double root = 1.0;  // (i+1)^0.7 = exp(0.7 ln(i+1)), by 40 Newton steps on x^10 = (i+1)^7
+            for (int it = 0; it < 60; ++it) {
+                double x9 = 1.0;
+                for (int k = 0; k < 9; ++k) x9 *= root;
+                root = root - (x9 * root - w) / (10.0 * x9);
+            }
+            acc += uint64_t(4294967296.0 / root);
+            code_cum[i] = acc;
+        }
+        return acc;
+    }();
+    static const char b64[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    SplitMix rng(mix(seed ^ 0x6D69786564ull, block));
+    size_t pos = 0;
+    while (pos < len) {
+        const uint64_t r = rng.next();
+        const int kind_r = int(r % 100);
+        size_t seg = size_t(256 + ((r >> 8) % 32768));
+        seg = std::min(seg, len - pos);
+        const size_t end = pos + seg;
+        if (kind_r < 30) {  // English-like text
+            while (pos < end) {
+                const int w = lx.draw(rng);
+                for (int k = 0; k < lx.len[w] && pos < end; ++k) out[pos++] = uint8_t(lx.words[w][k]);
+                const int q = int(rng.next() % 1000);
+                const char *sep = q < 850 ? " " : q < 900 ? ", " : q < 960 ? ". " : "\n";
+                for (const char *p = sep; *p && pos < end; ++p) out[pos++] = uint8_t(*p);
+            }
+        } else if (kind_r < 42) {  // code / markup
+            while (pos < end) {
+                const uint64_t u = rng.next() % code_total;
+                out[pos++] = uint8_t(code_syms[std::upper_bound(code_cum, code_cum + n_code, u) - code_cum]);
+            }
+        } else if (kind_r < 50) {  // UTF-8 two-byte script text with spaces
+            while (pos < end) {
+                uint64_t v = rng.next();
+                for (int k = 0; k < 6 && pos + 1 < end; ++k, v >>= 10) {
+                    if ((v & 7) == 0) { out[pos++] = ' '; continue; }
+                    out[pos++] = uint8_t(0xD0 + ((v >> 3) & 1));
+                    out[pos++] = uint8_t(0x80 + ((v >> 4) & 63));
+                }
+                if (pos + 1 == end) out[pos++] = ' ';
+            }
+        } else if (kind_r < 60) {  // base64
+            while (pos < end) {
+                uint64_t v = rng.next();
+                for (int k = 0; k < 10 && pos < end; ++k, v >>= 6) out[pos++] = uint8_t(b64[v & 63]);
+            }
+        } else {  // binary
+            while (pos < end) {
+                uint64_t v = rng.next();
+                for (int k = 0; k < 8 && pos < end; ++k, v >>= 8) out[pos++] = uint8_t(v);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -123,6 +198,24 @@ void blt_synth_text(uint8_t *out, size_t n, uint64_t seed, int threads) {
             for (size_t b = size_t(t); b < blocks; b += size_t(threads)) {
                 const size_t off = b * kTextBlock;
                 text_block(out + off, std::min(kTextBlock, n - off), seed, b);
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+}
+
+// Mixed corpus (see mixed_block): independent 1 MiB blocks.
+void blt_synth_mixed(uint8_t *out, size_t n, uint64_t seed, int threads) {
+    const size_t blocks = (n + kTextBlock - 1) / kTextBlock;
+    if (threads < 1) threads = 1;
+    lexicon();
+    mixed_block(nullptr, 0, seed, 0);  // builds the static tables before the threads start
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([=]() {
+            for (size_t b = size_t(t); b < blocks; b += size_t(threads)) {
+                const size_t off = b * kTextBlock;
+                mixed_block(out + off, std::min(kTextBlock, n - off), seed, b);
             }
         });
     }

@@ -155,6 +155,82 @@ def test_random_vs_oracle_all_variants(nat, torch_mod, oracle, variant, dense, m
     c.close()
 
 
+@pytest.mark.parametrize("variant", [3, 4])
+def test_fused_sweep_vs_oracle(nat, torch_mod, oracle, variant, monkeypatch):
+    """The single-pass sweep (count + look-back + emit in one kernel, fused.cuh): sizes around its tile and round
+    boundaries, ragged ends, every chunk size whose walls lie on tile boundaries, tables from no rule at all
+    (T_out = N_in, the staging line's worst case) to every pair (one run per chunk), and a chunk size it must
+    hand to the three-kernel sweep."""
+    monkeypatch.setenv("BLT_SWEEP_VARIANT", str(variant))
+    monkeypatch.setenv("BLT_DENSE", "0")
+    tile = 32768 if variant == 3 else 16384
+    c = nat.Context(0)
+    rng = random.Random(3000 + variant)
+    sizes = [1, 2, 15, 16, 17, 31, 33, 511, 512, 513, 4097, tile - 1, tile, tile + 1, tile + 15, tile + 16, tile + 17,
+             2 * tile - 1, 2 * tile, 3 * tile + 511, 40 * tile + 7777, 301 * tile + 12345, 16 * MiB, 37 * MiB + 1]
+    for n in sizes:
+        for density in (1.0, 0.85, 0.3, 0.0):
+            if n > 4 * MiB and density in (0.3,):
+                continue
+            alphabet = [97, 98, 99][: rng.choice([1, 2, 3])] if density == 1.0 else [97, 98, 99, 100, 32]
+            data, pairs = _random_case(rng, n, alphabet, density)
+            om = oracle.Merges(pairs)
+            s = c.bpe_from_pairs(pairs)
+            for chunk in (0, tile, 2 * tile, 8 * tile, 65536 + 16, 4 * MiB):
+                if chunk > n and chunk != 0:
+                    continue
+                want = oracle.run_buffer("bpe", data, chunk or max(n, 1), 8, om)
+                got, ends = resident(torch_mod, s, data, chunk)
+                assert got.size == want.size and np.array_equal(got, want), (variant, n, density, chunk)
+                cc = chunk or n
+                nck = (n + cc - 1) // cc
+                assert int(ends[-1]) == want.size
+                if nck <= 48:
+                    acc = 0
+                    for k in range(nck):
+                        acc += len(oracle.process_chunk("bpe", data[k * cc:(k + 1) * cc], om))
+                        assert int(ends[k]) == acc, (variant, n, chunk, k)
+            s.close()
+    c.close()
+
+
+@pytest.mark.parametrize("variant", [3, 4])
+def test_fused_long_runs(nat, torch_mod, oracle, variant, monkeypatch):
+    """Runs longer than a tile: every warp function and every tile function is the identity, so the carry has
+    to travel through the look-back chain; a run start at an odd offset flips every parity behind it."""
+    monkeypatch.setenv("BLT_SWEEP_VARIANT", str(variant))
+    monkeypatch.setenv("BLT_DENSE", "0")
+    c = nat.Context(0)
+    pairs = {(97, 97): 256, (97, 98): 257, (98, 97): 258, (98, 98): 259}
+    om = oracle.Merges(pairs)
+    s = c.bpe_from_pairs(pairs)
+    n = 6 * MiB + 5
+    for head in (0, 1, 2, 3):
+        data = np.full(n, 97, dtype=np.uint8)
+        data[:head] = 99
+        data[3 * MiB + 77] = 99
+        for chunk in (0, 2 * MiB, 1 * MiB + 65536):
+            got, _ = resident(torch_mod, s, data, chunk)
+            assert np.array_equal(got, oracle.run_buffer("bpe", data, chunk or n, 4, om)), (head, chunk)
+    ab = np.tile(np.frombuffer(b"ab", dtype=np.uint8), n // 2)
+    got, _ = resident(torch_mod, s, ab, 1 * MiB)
+    assert np.array_equal(got, oracle.run_buffer("bpe", ab, 1 * MiB, 4, om))
+    # capacity: an output that is one token short must be reported, and nothing may be written behind it
+    torch = torch_mod
+    data = np.random.default_rng(5).choice(np.array([97, 98, 99], dtype=np.uint8), size=200001)
+    want = oracle.run_buffer("bpe", data, 200001, 2, om)
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.full((want.size + 4096,), 0xA5, dtype=torch.uint8, device="cuda")
+    with pytest.raises(nat.BltError) as ei:
+        s.process_resident(d_in.data_ptr(), data.size, 0, d_out.data_ptr(), want.size - 2, 0, torch.cuda.current_stream().cuda_stream)
+    assert ei.value.code == nat.ERR_CAPACITY
+    assert bool((d_out[want.size - 2:] == 0xA5).all())
+    ln = s.process_resident(d_in.data_ptr(), data.size, 0, d_out.data_ptr(), want.size, 0, torch.cuda.current_stream().cuda_stream)
+    assert ln == want.size and np.array_equal(d_out[:ln].cpu().numpy(), want) and bool((d_out[want.size:] == 0xA5).all())
+    s.close()
+    c.close()
+
+
 def test_dense_predictor_sequence(ctx, torch_mod, oracle):
     """One strategy, inputs that flip between merge-dense and sparse: whichever path the predictor picks
     (dense attempt, device-launched exact sweep, host-launched exact sweep), the bytes are the oracle's."""
@@ -232,6 +308,24 @@ def test_basic_random_and_ragged(ctx, torch_mod, oracle):
             assert int(ends[-1]) == 2 * n
         assert np.array_equal(s.tokenize_host(data, chunk_size=1 << 22), want)
         assert np.array_equal(s.process_chunk(data), np.frombuffer(oracle.process_chunk("basic", data), dtype=np.uint8))
+
+
+def test_basic_output_aligned_to_16_not_32(ctx, torch_mod, oracle):
+    """The C ABI promises 16-byte alignment only: an output pointer that is 16 (mod 32) must not take the
+    32-byte store path (round-1 advisor finding: st.global.v8 faults on it, and the fault is sticky)."""
+    from blt_b200 import synth
+    torch = torch_mod
+    s = ctx.basic()
+    for n in (16, 4096 + 5, 3 * MiB + 17):
+        data = synth.random_bytes(n, 123 + n)
+        d_in = torch.from_numpy(data).cuda()
+        d_buf = torch.full((2 * n + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        off = 16 if d_buf.data_ptr() % 32 == 0 else 32 - (d_buf.data_ptr() % 32) + 16
+        ln = s.process_resident(d_in.data_ptr(), n, 0, d_buf.data_ptr() + off, 2 * n, 0, torch.cuda.current_stream().cuda_stream)
+        assert ln == 2 * n and (d_buf.data_ptr() + off) % 32 == 16
+        h = d_buf.cpu().numpy()
+        assert np.array_equal(h[off:off + 2 * n], oracle.run_buffer("basic", data, 1 << 22, 2))
+        assert np.all(h[:off] == 0xA5) and np.all(h[off + 2 * n:] == 0xA5)
 
 
 def test_empty_and_capacity_errors(ctx, nat, torch_mod):
@@ -529,7 +623,7 @@ def test_pair_histogram_and_training(ctx, torch_mod):
         assert np.array_equal(l, wl) and np.array_equal(r, wr), k
 
 
-@pytest.mark.parametrize("variant,dense", [(0, "0"), (1, "0"), (2, "0"), (0, "always")])
+@pytest.mark.parametrize("variant,dense", [(0, "0"), (1, "0"), (2, "0"), (0, "always"), (3, "0"), (4, "0"), (3, "always")])
 def test_no_writes_outside_the_buffers(nat, torch_mod, oracle, variant, dense, monkeypatch):
     """Input, output (capacity exactly 2n) and chunk_ends (exactly one entry per chunk) sit between canaries
     in one allocation: ragged sizes and tiny chunks must leave every canary and the input intact.  (Found by
@@ -546,7 +640,8 @@ def test_no_writes_outside_the_buffers(nat, torch_mod, oracle, variant, dense, m
     al = lambda x: (x + 255) // 256 * 256
     stream = torch.cuda.current_stream().cuda_stream
     for n, chunk in ((6, 0), (15, 0), (21, 0), (35, 16), (253, 2), (253, 16), (2119, 16), (4095, 2047), (4097, 4096),
-                     (2 * 4096 - 5, 4096), (70001, 1000), (1 * MiB + 9, 65536)):
+                     (2 * 4096 - 5, 4096), (70001, 1000), (1 * MiB + 9, 65536),
+                     (32768, 0), (32769, 32768), (3 * 32768 + 17, 32768), (5 * 16384 - 1, 16384), (1 * MiB + 9, 0)):
         data = rng.choice(np.array([97, 98, 99], dtype=np.uint8), size=n)
         eff = chunk if chunk and chunk < n else n
         nc = (n + eff - 1) // eff

@@ -24,7 +24,7 @@ index = args.only if args.only >= 0 else 0
 while time.time() < t_end:
     rng = random.Random(args.seed * 1000003 + index)
     nrng = np.random.default_rng(args.seed * 1000003 + index)
-    os.environ["BLT_SWEEP_VARIANT"] = str(rng.choice([0, 1, 2]))
+    os.environ["BLT_SWEEP_VARIANT"] = str(rng.choice([0, 1, 2, 3, 3, 4, 4]))
     os.environ["BLT_DENSE"] = rng.choice(["0", "1", "always"])
     ctx = nat.Context(0)
     alpha = rng.choice([2, 3, 5, 26, 256])
@@ -51,7 +51,7 @@ while time.time() < t_end:
     pairs = {k: 256 + gap * i for i, k in enumerate(keys) if 256 + gap * i < 65536}
     om = ora.Merges(pairs)
     s = ctx.bpe_from_pairs(pairs)
-    chunk = rng.choice([0, 2, 16, 100, 4096, 4098, 65536, 100001, 1 << 20])
+    chunk = rng.choice([0, 0, 2, 16, 100, 4096, 4098, 16384, 32768, 65536, 100001, 1 << 20])
     eff = chunk if chunk and chunk < n else max(n, 1)
     want = ora.run_buffer("bpe", data, eff, 4, om)
     ok = True
