@@ -112,4 +112,9 @@ class ByteTokenizer:
                    _rust_opt(self.threads), _rust_opt(self.chunk_size), _rust_opt(self.memory_cap)))
 
 
-__version__ = version()
+def __getattr__(name):
+    # `blt.__version__` (blt_python/python/blt/__init__.py:16), resolved on first use: importing the package (for
+    # instance for blt_b200.synth, the workload generators) must not load libblt_cuda.so.
+    if name == "__version__":
+        return version()
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -238,6 +238,16 @@ int run_detok(blt_strategy *s, Workspace &ws, const uint8_t *d_tokens, size_t n_
 
 }  // namespace bltc
 
+void blt_strategy::settle_pending() {
+    // resident_mu is held.  Waits for the pending call's stream, reads its result back and keeps it for its thread.
+    bltc::DeviceResult r = resident_result;
+    r.rc = bltc::finish_result(resident, resident_stream, &r);
+    if (r.rc == BLT_OK && cudaStreamSynchronize(resident_stream) != cudaSuccess) r.rc = bltc::fail(BLT_ERR_CUDA, "cudaStreamSynchronize failed");
+    if (r.rc != BLT_OK) r.err = bltc::g_last_error;
+    resident_settled[resident_owner] = r;
+    resident_pending = false;
+}
+
 bool blt_strategy::want_dense() {
     if (!try_dense) return false;
     if (dense_always) return true;
@@ -462,6 +472,8 @@ int blt_process_resident(blt_strategy *s, const void *d_in, size_t n, size_t chu
     std::lock_guard<std::mutex> lk(s->resident_mu);
     CUDA_TRY(cudaSetDevice(s->ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (s->resident_pending && (s->resident_owner != std::this_thread::get_id() || s->resident_stream != st)) s->settle_pending();
+    s->resident_pending = false;
     int rc = run_device(s, s->resident, static_cast<const uint8_t *>(d_in), n, chunk_size, static_cast<uint8_t *>(d_out),
                         out_cap, d_chunk_ends, st, &s->resident_result);
     if (rc) return rc;
@@ -470,7 +482,12 @@ int blt_process_resident(blt_strategy *s, const void *d_in, size_t n, size_t chu
         if (rc) return rc;
         if (s->resident_result.kind == DeviceResult::KNOWN) CUDA_TRY(cudaStreamSynchronize(st));
         *out_len = s->resident_result.len;
+        return BLT_OK;
     }
+    s->resident_pending = true;
+    s->resident_owner = std::this_thread::get_id();
+    s->resident_stream = st;
+    s->resident_settled.erase(s->resident_owner);
     return BLT_OK;
 }
 
@@ -495,6 +512,8 @@ int blt_detokenize_resident(blt_strategy *s, const void *d_tokens, size_t n_byte
     std::lock_guard<std::mutex> lk(s->resident_mu);
     CUDA_TRY(cudaSetDevice(s->ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (s->resident_pending && (s->resident_owner != std::this_thread::get_id() || s->resident_stream != st)) s->settle_pending();
+    s->resident_pending = false;
     int rc = run_detok(s, s->resident, static_cast<const uint8_t *>(d_tokens), n_bytes, static_cast<uint8_t *>(d_out), out_cap,
                        st, &s->resident_result);
     if (rc) return rc;
@@ -503,7 +522,12 @@ int blt_detokenize_resident(blt_strategy *s, const void *d_tokens, size_t n_byte
         if (rc) return rc;
         if (s->resident_result.kind == DeviceResult::KNOWN) CUDA_TRY(cudaStreamSynchronize(st));
         *out_len = s->resident_result.len;
+        return BLT_OK;
     }
+    s->resident_pending = true;
+    s->resident_owner = std::this_thread::get_id();
+    s->resident_stream = st;
+    s->resident_settled.erase(s->resident_owner);
     return BLT_OK;
 }
 
@@ -559,9 +583,27 @@ int blt_resident_result(blt_strategy *s, void *stream, size_t *out_len, uint32_t
     std::lock_guard<std::mutex> lk(s->resident_mu);
     CUDA_TRY(cudaSetDevice(s->ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const std::thread::id me = std::this_thread::get_id();
+    if (!(s->resident_pending && s->resident_owner == me)) {
+        // settled on this thread's behalf by a later call of another thread, or collected before
+        auto it = s->resident_settled.find(me);
+        if (it == s->resident_settled.end()) {
+            if (s->resident_pending) return fail(BLT_ERR_INVALID_INPUT, "no device-resident call of this thread is outstanding");
+            // no asynchronous call outstanding: the most recent (synchronous or collected) call of the strategy
+            if (out_len) *out_len = s->resident_result.len;
+            if (sweeps) *sweeps = s->resident_result.sweeps;
+            return BLT_OK;
+        }
+        const DeviceResult r = it->second;
+        if (r.rc != BLT_OK) return fail(r.rc, r.err);
+        if (out_len) *out_len = r.len;
+        if (sweeps) *sweeps = r.sweeps;
+        return BLT_OK;
+    }
     int rc = finish_result(s->resident, st, &s->resident_result);
-    if (rc) return rc;
+    if (rc) { s->resident_pending = false; return rc; }
     CUDA_TRY(cudaStreamSynchronize(st));
+    s->resident_pending = false;
     if (out_len) *out_len = s->resident_result.len;
     if (sweeps) *sweeps = s->resident_result.sweeps;
     return BLT_OK;

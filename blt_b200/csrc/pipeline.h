@@ -6,7 +6,9 @@
 #include "kernels.cuh"
 
 #include <atomic>
+#include <map>
 #include <memory>
+#include <thread>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -38,6 +40,8 @@ struct DeviceResult {
     int launches = 0;     // kernels enqueued by the host
     blt_strategy *owner = nullptr;  // set when the dense pass was attempted: decode_ctrl reports back to it
     uint32_t len_scale = 2;         // bytes per unit of the device's total (2: tokens, 1: detokenizer bytes)
+    int rc = 0;                     // a result settled on its caller's behalf: the code and message it ended with
+    std::string err;
 };
 
 int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, size_t chunk, uint8_t *d_out,
@@ -107,8 +111,18 @@ struct blt_strategy {
     uint32_t detok_limit = 0, detok_holes = 0;
     int detok_state = 0;                  //   0 not built, 1 ready, < 0 the error code it failed with
     int ensure_detok();
+    // blt_process_resident / blt_detokenize_resident share ONE workspace (control block, descriptors).  An
+    // asynchronous call (out_len == NULL) stays "pending" until its result is collected; a call from another thread
+    // or on another stream first settles the pending one (waits for it, reads its result back and files it under
+    // the thread that made it), so two calls never run on the scratch at once and blt_resident_result returns the
+    // calling thread's own most recent call.  Calls of one thread on one stream are ordered by the stream itself.
     std::mutex resident_mu;
     bltc::Workspace resident;             // workspace of blt_process_resident
-    bltc::DeviceResult resident_result;
+    bltc::DeviceResult resident_result;   // of the pending call
+    bool resident_pending = false;
+    std::thread::id resident_owner;
+    cudaStream_t resident_stream = nullptr;
+    std::map<std::thread::id, bltc::DeviceResult> resident_settled;
+    void settle_pending();                // resident_mu held
     ~blt_strategy();
 };

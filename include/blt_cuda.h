@@ -113,12 +113,18 @@ BLT_API int blt_tokenize_host(blt_strategy *s, const uint8_t *in, size_t n, size
  *   out_len      : optional HOST pointer; if non-NULL the call synchronises `stream` and stores the
  *                  total output length in bytes.  If NULL the call returns as soon as the work is
  *                  enqueued (use blt_resident_result afterwards).
+ * One strategy owns one device workspace: asynchronous calls of one thread on one stream simply queue
+ * up behind each other; a call from another thread or on another stream first waits for the
+ * outstanding one (its result is kept for the thread that made it).  For truly concurrent device-
+ * resident work create one strategy per stream (the table is 128 KiB).
+ * Basic mode stores 32 bytes at a time when d_out is 32-byte aligned and 16 at a time otherwise.
  * This is the call bench.py times as `value` (inputs already in HBM). */
 BLT_API int blt_process_resident(blt_strategy *s, const void *d_in, size_t n, size_t chunk_size,
                                  void *d_out, size_t out_cap, uint64_t *d_chunk_ends, void *stream,
                                  size_t *out_len);
 /* Synchronises `stream` and returns the output length (bytes) and the number of BPE sweeps of the
- * most recent blt_process_resident call made on this strategy by the calling thread. */
+ * most recent blt_process_resident / blt_detokenize_resident call made on this strategy by the
+ * calling thread (also when a later call of another thread had to wait for it in the meantime). */
 BLT_API int blt_resident_result(blt_strategy *s, void *stream, size_t *out_len, uint32_t *sweeps);
 
 /* ---- detokenizer: big-endian u16 tokens -> bytes ------------------------------------

@@ -159,11 +159,11 @@ def test_random_vs_oracle_all_variants(nat, torch_mod, oracle, variant, dense, m
 def test_fused_sweep_vs_oracle(nat, torch_mod, oracle, variant, monkeypatch):
     """The single-pass sweep (count + look-back + emit in one kernel, fused.cuh): sizes around its tile and round
     boundaries, ragged ends, every chunk size whose walls lie on tile boundaries, tables from no rule at all
-    (T_out = N_in, the staging line's worst case) to every pair (one run per chunk), and a chunk size it must
-    hand to the three-kernel sweep."""
+    (T_out = N_in, the staging line's worst case) to every pair (one run per chunk), chunk walls on and inside
+    tiles, and a chunk size shorter than a tile, which it must hand to the three-kernel sweep."""
     monkeypatch.setenv("BLT_SWEEP_VARIANT", str(variant))
     monkeypatch.setenv("BLT_DENSE", "0")
-    tile = 32768 if variant == 3 else 16384
+    tile = 30720 if variant == 3 else 16384   # 15 or 8 worker warps x 4 rounds x 512 bytes
     c = nat.Context(0)
     rng = random.Random(3000 + variant)
     sizes = [1, 2, 15, 16, 17, 31, 33, 511, 512, 513, 4097, tile - 1, tile, tile + 1, tile + 15, tile + 16, tile + 17,
@@ -176,7 +176,7 @@ def test_fused_sweep_vs_oracle(nat, torch_mod, oracle, variant, monkeypatch):
             data, pairs = _random_case(rng, n, alphabet, density)
             om = oracle.Merges(pairs)
             s = c.bpe_from_pairs(pairs)
-            for chunk in (0, tile, 2 * tile, 8 * tile, 65536 + 16, 4 * MiB):
+            for chunk in (0, tile, 2 * tile, 8 * tile, 65536 + 16, 100001, 4 * MiB, 4000):
                 if chunk > n and chunk != 0:
                     continue
                 want = oracle.run_buffer("bpe", data, chunk or max(n, 1), 8, om)

@@ -7,6 +7,7 @@ import json
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -151,6 +152,41 @@ def test_python_surface_shape():
         blt_b200.ByteTokenizer(memory_cap=150)
     with pytest.raises(IOError):
         blt_b200.load_bpe_merges("non_existent_file.txt")
+
+
+def test_blt_alias_package_and_lazy_library():
+    """`import blt` is the reference's module name (blt_python/python/blt/__init__.py:12-16); importing the package or
+    the workload generators must not map libblt_cuda.so (bench.py's reference arm relies on it)."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import blt, blt_b200\n"
+            "from blt_b200 import synth\n"
+            "assert blt.ByteTokenizer is blt_b200.ByteTokenizer and blt.load_bpe_merges is blt_b200.load_bpe_merges\n"
+            "assert sorted(blt.__all__) == ['ByteTokenizer', '__version__', 'load_bpe_merges', 'version']\n"
+            "d = synth.mixed(1 << 16)\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libblt_cuda' not in maps, 'importing the package loaded the CUDA library'\n"
+            "assert blt.__version__ == blt.version() == '0.2.2'\n"
+            "assert 'libblt_cuda' in open('/proc/self/maps').read()\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_rust_shim_binds_only_declared_symbols():
+    """integration/rust/*.rs (untested: no Rust toolchain here) may only bind functions the header declares and the
+    library exports, with the header's arity."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "blt_cuda.h")).read()
+    lib = nat.lib()
+    for f in ("cuda_strategy.rs", "select_strategy.rs"):
+        src = open(os.path.join(ROOT, "integration", "rust", f)).read()
+        for name, args in re.findall(r"fn (blt_\w+)\(([^)]*)\)", src):
+            assert hasattr(lib, name), name
+            m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, hdr, re.S)
+            assert m, name
+            n_rust = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
+            c_args = m.group(1).strip()
+            n_c = 0 if c_args in ("", "void") else len(c_args.split(","))
+            assert n_rust == n_c, (name, n_rust, n_c)
 
 
 # ---- no CPU fallback --------------------------------------------------------------------------------
