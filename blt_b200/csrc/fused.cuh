@@ -1,30 +1,32 @@
 // fused.cuh -- the exact sweep in ONE pass: count, decoupled look-back and emit fused in a single persistent kernel.
 //
 // The input is read from DRAM once (N_in + 2*T_out bytes of traffic = the algorithmic bytes) and every pair is
-// looked up once.  One CTA per SM holds the 128 KiB pair table and takes tiles of WG*R*512 input bytes in ticket
-// order (one global counter).  WG worker warps and one chain warp (warp specialisation), one barrier per tile:
+// looked up once.  One CTA per SM holds the 128 KiB pair table; tiles of WG*R*512 input bytes are dealt to the CTAs
+// round-robin.  WG worker warps and one chain warp (warp specialisation); they meet on mbarriers only (a worker
+// never waits for another worker):
 //
-//   stage   the tile is copied into the CTA's shared-memory buffer by cp.async.bulk (issued by the chain warp as
-//           soon as the workers have counted the previous tile, completion on an mbarrier);
+//   stage   every worker copies its own slice of the next tile into its shared-memory buffer with cp.async.bulk
+//           (one elected lane, completion on the worker's mbarrier) as soon as it has counted the current one, so the
+//           copy has the whole emit phase to land;
 //   count   every worker owns R*512 consecutive bytes of the tile (R rounds of 32 lanes x 16 bytes): both parities
 //           are looked up, the tokens STAY IN REGISTERS, run parity is resolved inside the warp with two ballots
 //           per round under the hypothesis "the warp's carry_in is 0" and the warp's slice is reduced to one carry
 //           function (identity / constant, tokens for carry_in 0, the 0/1-token delta for carry_in 1);
 //   chain   while the workers emit tile i-1 and count tile i+1, the chain warp composes the WG warp functions of
-//           tile i, publishes the tile's function (status A) in the tile's 64-bit descriptor and polls the 64
+//           tile i, publishes the tile's function (status A) in the tile's 64-bit descriptor and polls the 192
 //           descriptors in front of it until it sees an inclusive prefix (status P) with nothing missing behind it.
-//           The carry entering every tile of the window comes from two ballots (nearest non-identity tile in front
-//           of it), its exact token count is cnt0 - (delta & carry_in), and one warp-wide add gives the offset: the
-//           chain advances up to 64 tiles per hop.  Chunk walls lie on tile boundaries, where the carry is 0 by
-//           definition; chunk_ends fall out of the inclusive prefixes.  The look-back has a whole tile period of
-//           slack before anybody needs its result, so nobody waits for it in the steady state;
-//   emit    (one tile behind) every worker compacts its retained tokens into a warp-private staging line
-//           (XOR-swizzled so that the 32 lanes' 2-byte stores spread over the banks) and streams whole 4-byte
-//           words out.  Only the lanes in front of the slice's first non-identity segment depend on the carry_in;
-//           they are redone when it is 1.
+//           The carry entering every tile of the window comes from ballots (nearest non-identity tile in front of
+//           it), its exact token count is cnt0 - (delta & carry_in), and one warp-wide add gives the offset.  The
+//           window spans more than one round of the deal, so nothing propagates hop by hop inside a round: a tile
+//           is resolved one poll after the tiles dealt with it have published.  The look-back has a whole tile
+//           period of slack before anybody needs its result;
+//   emit    (one tile behind) every worker compacts the retained tokens of its whole slice into a warp-private
+//           staging line (XOR-swizzled so that the 32 lanes' 2-byte stores spread over the banks; the R rounds are
+//           R independent store chains) and streams whole 4-byte words out.  Only the lanes in front of the
+//           slice's first non-identity segment depend on the carry_in; they are redone when it is 1.
 //
-// Forward progress: a tile only ever waits for tiles with smaller tickets, which are held by resident CTAs, and
-// nothing that publishes a tile's function waits for anything.
+// Forward progress: a tile only ever waits for tiles with smaller numbers, which belong to resident CTAs that reach
+// them before any larger one, and nothing that publishes a tile's function waits for anything.
 // Included by kernels.cu inside its anonymous namespace, after sweep3.cuh (ScanFn, scan_compose, start_bits).
 #pragma once
 
@@ -35,8 +37,9 @@ constexpr unsigned long long FZ_COUNT = (1ull << 56) - 1;
 constexpr uint32_t FZ_F_START = 2u, FZ_NO_WALL = 0xffffffffu;
 
 struct FusedShared {
-    unsigned long long mbar;           // completion of the bulk copy into the tile buffer
-    uint32_t tile[2];                  // ticket of iteration i in tile[i & 1]
+    unsigned long long wbar[16];       // per worker: completion of the bulk copy of its slice
+    unsigned long long counted[2];     // every worker has counted the tile of iteration i (slot i & 1): WG arrivals
+    unsigned long long resolved[2];    // the chain warp has left that tile's prefix in res[i & 1]: one arrival
     uint32_t flags[2];                 // FZ_F_START: it starts a chunk (the carry entering it is 0)
     uint32_t wall[2][2];               // offsets of the (at most two) chunk-last elements inside the tile, else FZ_NO_WALL:
                                        //   [0] a chunk boundary, [1] the end of the input if it is another element
@@ -51,13 +54,16 @@ template <int WG, int R>
 struct FusedCfg {
     static_assert(WG <= 16, "the chain warp scans the worker functions in one half warp");
     static_assert((WG * R * 512) % 16 == 0, "tiles start on 16-byte boundaries");
+    static_assert(R % 2 == 0, "the emit scan packs two rounds per word");
     static constexpr int THREADS = (WG + 1) * 32;  // WG workers + the chain warp
+    static constexpr int LB = 6;  // look-back window: 32 * LB tiles (more than the 148 tiles of one round of the deal)
     static constexpr int WARP_BYTES = R * 512;
     static constexpr int TILE = WG * WARP_BYTES;
-    static constexpr int BUF = TILE + 128;     // + the look-ahead vector
-    static constexpr int STAGE_BYTES = 2048;   // per worker: 1 pending + 512 new tokens in a 1 KiB-aligned line
-    static constexpr int OFF_STAGE = PairsFE::TABLE_BYTES;  // + up to 1 KiB of alignment slack
-    static constexpr int OFF_BUF = OFF_STAGE + WG * STAGE_BYTES + 1024;
+    static constexpr int WBUF = WARP_BYTES + 128;  // a worker's slice + the look-ahead vector
+    static constexpr int BUF = WG * WBUF;
+    static constexpr int STAGE_BYTES = (2 * (1 + R * 512) + 127) / 128 * 128;  // per worker: 1 pending + R*512 new tokens
+    static constexpr int OFF_STAGE = PairsFE::TABLE_BYTES;  // + up to 128 bytes of alignment slack
+    static constexpr int OFF_BUF = OFF_STAGE + WG * STAGE_BYTES + 128;
     static constexpr int OFF_GS = OFF_BUF + BUF;
     static constexpr int SMEM = OFF_GS + 1024;
     static_assert(sizeof(FusedShared) <= 1024, "control block");
@@ -94,7 +100,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void cta_bar(int threads) { asm volatile("bar.sync 0, %0;" ::"r"(threads) : "memory"); }
 __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -120,7 +125,7 @@ __device__ __forceinline__ uint32_t lds_tbl(uint32_t addr) {
 }
 // staging line: shared address of a token -> where it really lives.  Bank bits 2-4 are XORed with the index of the
 // 128-byte window (mod 8), so that stores 4 to 8 words apart (one lane's tokens behind the other's) do not pile up on
-// a few banks.  Lines are 1 KiB aligned, so window i of a line is XORed with i & 7.
+// a few banks.  Every 128-byte window is permuted within itself: lines are whole, 128-byte aligned windows.
 __device__ __forceinline__ uint32_t stage_swz(uint32_t addr) { return addr ^ ((addr >> 5) & 0x1Cu); }
 
 // The SEG/2 pairs of one 16-byte segment that start at positions of parity PAR: the big-endian u16 to emit at each of
@@ -132,9 +137,11 @@ __device__ __forceinline__ void fz_lookup(uint32_t tbl_s, const uint4 &w, uint32
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t y = W[k] ^ ((W[k] >> 7) & 0x01FF01FFu);  // pair_table_index of both halves at once
-        const uint32_t e0 = lds_tbl(tbl_s + ((y & 0xFFFFu) << 1));
-        const uint32_t e1 = lds_tbl(tbl_s + ((y >> 16) << 1));
-        vals[k] = __byte_perm(e0, e1, 0x5410);
+        // entry address = table + 2 * index: one multiply-add per entry (the compiler's own form is shift, mask, add)
+        uint32_t a0, a1;
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a0) : "r"(y & 0xFFFFu), "r"(tbl_s));
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a1) : "r"(y >> 16), "r"(tbl_s));
+        vals[k] = __byte_perm(lds_tbl(a0), lds_tbl(a1), 0x5410);
     }
 }
 
@@ -150,40 +157,39 @@ __device__ __forceinline__ uint32_t fz_membership(const uint32_t *hv, const uint
     return (p[0] >> 28) | ((p[1] >> 24) & 0xF0u) | ((p[2] >> 20) & 0xF00u) | ((p[3] >> 16) & 0xF000u);
 }
 
-// Chain lane 0: starts the copy of tile `t` into the buffer.  Whole 16-byte vectors go through the bulk copy (tile +
-// look-ahead vector where the input has them); the < 16 ragged bytes of the input's end are left to fz_copy_tail,
-// which the whole chain warp runs.
+// A worker starts the copy of its slice of tile `t` into its own buffer.  Whole 16-byte vectors go through the bulk
+// copy (slice + look-ahead vector where the input has them); the < 16 ragged bytes at the input's end are copied by
+// the lanes themselves first (the barrier's arrive releases them).
 template <class C>
-__device__ __forceinline__ void fz_issue_copy(const SweepArgs &a, uint32_t t, unsigned char *buf, uint32_t bar) {
-    const unsigned long long base = (unsigned long long)t * C::TILE;
-    const unsigned long long left = a.n - base;
-    const uint32_t avail = left < (unsigned long long)(C::TILE + 16) ? uint32_t(left) : uint32_t(C::TILE + 16);
+__device__ __forceinline__ void fz_warp_copy(const SweepArgs &a, uint32_t t, int wg, unsigned char *wbuf, uint32_t wbar, int lane) {
+    const unsigned long long base = (unsigned long long)t * C::TILE + (unsigned long long)wg * C::WARP_BYTES;
+    uint32_t avail = 0;
+    if (base < a.n) {
+        const unsigned long long left = a.n - base;
+        avail = left < (unsigned long long)(C::WARP_BYTES + 16) ? uint32_t(left) : uint32_t(C::WARP_BYTES + 16);
+    }
     const uint32_t bytes16 = avail & ~15u;
-    if (bytes16 != 0) {
-        mbar_expect_tx(bar, bytes16);
-        bulk_g2s(smem_u32(buf), static_cast<const unsigned char *>(a.in) + base, bytes16, bar);
-    } else {
-        mbar_arrive(bar);
+    if (bytes16 + lane < avail) wbuf[bytes16 + lane] = static_cast<const unsigned char *>(a.in)[base + bytes16 + lane];
+    __syncwarp();
+    if (lane == 0) {
+        if (bytes16 != 0) {
+            mbar_expect_tx(wbar, bytes16);
+            bulk_g2s(smem_u32(wbuf), static_cast<const unsigned char *>(a.in) + base, bytes16, wbar);
+        } else {
+            mbar_arrive(wbar);
+        }
     }
 }
-template <class C>
-__device__ __forceinline__ void fz_copy_tail(const SweepArgs &a, uint32_t t, unsigned char *buf, int lane) {
-    const unsigned long long base = (unsigned long long)t * C::TILE;
-    const unsigned long long left = a.n - base;
-    if (left >= (unsigned long long)(C::TILE + 16)) return;
-    const uint32_t avail = uint32_t(left);
-    const uint32_t bytes16 = avail & ~15u;
-    if (bytes16 + lane < avail) buf[bytes16 + lane] = static_cast<const unsigned char *>(a.in)[base + bytes16 + lane];
-}
+
 // Where tile t meets chunk walls - chain lane 0.  Chunks are at least a tile long, so a tile holds at most one chunk
 // boundary; the input's last tile may hold the end of the input as well.
 template <class C>
-__device__ __forceinline__ void fz_tile_geometry(const SweepArgs &a, unsigned long long chunk, uint32_t t, uint32_t n_tiles,
+__device__ __forceinline__ void fz_tile_geometry(const SweepArgs &a, unsigned long long chunk, unsigned long long t, uint32_t n_tiles,
                                                  FusedShared *gs, uint32_t slot) {
     uint32_t flags = 0, wall0 = FZ_NO_WALL, wall1 = FZ_NO_WALL, len = 0;
     unsigned long long ck = 0;
     if (t < n_tiles) {
-        const unsigned long long base = (unsigned long long)t * C::TILE;
+        const unsigned long long base = t * C::TILE;
         len = (a.n - base < (unsigned long long)C::TILE) ? uint32_t(a.n - base) : uint32_t(C::TILE);
         ck = base / chunk;
         if (base - ck * chunk == 0) flags |= FZ_F_START;
@@ -199,12 +205,19 @@ __device__ __forceinline__ void fz_tile_geometry(const SweepArgs &a, unsigned lo
     gs->wall_ck[slot][1] = (a.n - 1) / chunk;
 }
 
-// ---- the chain warp: one call per tile -------------------------------------------------------------------------
-// Composes the worker functions of tile `cur` (gs->fn_*[par]), publishes A, then resolves the tile's prefix by
-// look-back, publishes P and leaves every worker's (carry_in, offset) in gs->res[par].
+// ---- the chain warp ------------------------------------------------------------------------------------------
+// A tile between "its function is published" and "its prefix is resolved".
+struct FzPending {
+    ScanFn tf;       // the whole tile
+    ScanFn ex;       // lane w: workers 0 .. w-1 composed
+    uint32_t cur, par, starts;
+};
+
+// Composes the worker functions of tile `cur` (gs->fn_*[par]) and publishes the tile's function (status A).  Never
+// waits for anything: other tiles' look-backs depend on it.
 template <int WG>
-__device__ __forceinline__ void fz_chain_tile(const SweepArgs &a, FusedShared *gs, unsigned long long *desc, uint32_t cur,
-                                              uint32_t flags, uint32_t par, uint32_t n_tiles, int lane) {
+__device__ __forceinline__ FzPending fz_chain_publish(FusedShared *gs, unsigned long long *desc, uint32_t cur, uint32_t flags,
+                                                      uint32_t par, int lane) {
     ScanFn item;
     item.id = 1; item.cst = 0; item.delta = 0; item.cnt0 = 0;
     if (lane < WG) {
@@ -218,75 +231,96 @@ __device__ __forceinline__ void fz_chain_tile(const SweepArgs &a, FusedShared *g
         const ScanFn o = scan_shfl_up(inc, s);
         if (lane >= s) inc = scan_compose(o, inc);
     }
-    ScanFn ex = scan_shfl_up(inc, 1);
-    if (lane == 0) { ex.id = 1; ex.cst = 0; ex.delta = 0; ex.cnt0 = 0; }
-    ScanFn tf;  // the whole tile
+    FzPending pd;
+    pd.ex = scan_shfl_up(inc, 1);
+    if (lane == 0) { pd.ex.id = 1; pd.ex.cst = 0; pd.ex.delta = 0; pd.ex.cnt0 = 0; }
     {
         const uint32_t packed = inc.id | (inc.cst << 1) | (inc.delta << 2);
         const uint32_t p = __shfl_sync(FULL, packed, WG - 1);
-        tf.id = p & 1u; tf.cst = (p >> 1) & 1u; tf.delta = (p >> 2) & 1u;
-        tf.cnt0 = __shfl_sync(FULL, inc.cnt0, WG - 1);
+        pd.tf.id = p & 1u; pd.tf.cst = (p >> 1) & 1u; pd.tf.delta = (p >> 2) & 1u;
+        pd.tf.cnt0 = __shfl_sync(FULL, inc.cnt0, WG - 1);
     }
-    const bool starts = (flags & FZ_F_START) != 0;
-    if (starts) {  // the carry entering a chunk is 0: the tile's function collapses to a constant
-        tf.cst = tf.id ? 0u : tf.cst;
-        tf.id = 0; tf.delta = 0;
+    pd.cur = cur; pd.par = par;
+    pd.starts = (flags & FZ_F_START) ? 1u : 0u;
+    if (pd.starts) {  // the carry entering a chunk is 0: the tile's function collapses to a constant
+        pd.tf.cst = pd.tf.id ? 0u : pd.tf.cst;
+        pd.tf.id = 0; pd.tf.delta = 0;
     }
     if (lane == 0)
-        st_desc(desc + cur, FZ_A | (tf.id ? FZ_A_ID : 0ull) | (tf.cst ? FZ_A_CST : 0ull) | (tf.delta ? FZ_A_DELTA : 0ull) | tf.cnt0);
-    // look-back over the 64 tiles in front: position x <-> tile cur-1-x; lane i holds positions i and i+32
-    uint32_t c_in = 0;
-    unsigned long long base = 0;
-    {
-        const long long i0 = (long long)cur - 1 - lane, i1 = i0 - 32;
-        unsigned long long d0 = FZ_P, d1 = FZ_P;  // in front of tile 0: carry 0, nothing emitted
-        uint32_t polls = 0;
-        for (;;) {
-            if (i0 >= 0) d0 = ld_desc(desc + i0);
-            if (i1 >= 0) d1 = ld_desc(desc + i1);
-            const uint32_t s0 = uint32_t(d0 >> 62), s1 = uint32_t(d1 >> 62);
-            const unsigned long long pm =
-                (unsigned long long)__ballot_sync(FULL, s0 == 2u) | ((unsigned long long)__ballot_sync(FULL, s1 == 2u) << 32);
-            const unsigned long long zm =
-                (unsigned long long)__ballot_sync(FULL, s0 == 0u) | ((unsigned long long)__ballot_sync(FULL, s1 == 0u) << 32);
-            if (pm != 0ull) {
-                const int q = __ffsll((long long)pm) - 1;  // the nearest inclusive prefix
-                const unsigned long long nearer = (1ull << q) - 1ull;
-                if ((zm & nearer) == 0ull) {
-                    // the carry leaving position x: P.carry at q, the constant of a non-identity tile, else whatever enters it
-                    unsigned long long nim = (unsigned long long)__ballot_sync(FULL, (d0 & FZ_A_ID) == 0ull) |
-                                             ((unsigned long long)__ballot_sync(FULL, (d1 & FZ_A_ID) == 0ull) << 32);
-                    const unsigned long long cm = (unsigned long long)__ballot_sync(FULL, (d0 & FZ_A_CST) != 0ull) |
-                                                  ((unsigned long long)__ballot_sync(FULL, (d1 & FZ_A_CST) != 0ull) << 32);
-                    nim = (nim & nearer) | (1ull << q);
-                    // the carry entering position x leaves the nearest non-identity position behind it (x+1 .. q)
-                    const unsigned long long above0 = nim >> (lane + 1);
-                    const int j0 = lane + __ffsll((long long)above0);
-                    const uint32_t cin0 = uint32_t((cm >> (j0 & 63)) & 1ull);
-                    const unsigned long long above1 = (lane < 31) ? (nim >> (lane + 33)) : 0ull;
-                    const int j1 = lane + 32 + __ffsll((long long)above1);
-                    const uint32_t cin1 = uint32_t((cm >> (j1 & 63)) & 1ull);
-                    uint32_t e = 0;
-                    if (lane < q) e += uint32_t(d0 & 0xffffffffull) - (((d0 & FZ_A_DELTA) && cin0) ? 1u : 0u);
-                    if (lane + 32 < q) e += uint32_t(d1 & 0xffffffffull) - (((d1 & FZ_A_DELTA) && cin1) ? 1u : 0u);
-                    e = __reduce_add_sync(FULL, e);
-                    const unsigned long long pd0 = __shfl_sync(FULL, d0, q & 31), pd1 = __shfl_sync(FULL, d1, q & 31);
-                    base = ((q < 32 ? pd0 : pd1) & FZ_COUNT) + e;
-                    const unsigned long long low = nim & (0ull - nim);  // the nearest non-identity position (q at the latest)
-                    c_in = (cm & low) ? 1u : 0u;                        // its carry enters this tile
-                    break;
-                }
+        st_desc(desc + cur, FZ_A | (pd.tf.id ? FZ_A_ID : 0ull) | (pd.tf.cst ? FZ_A_CST : 0ull) | (pd.tf.delta ? FZ_A_DELTA : 0ull) | pd.tf.cnt0);
+    return pd;
+}
+
+// One poll of the look-back of a pending tile.  On success: publishes its inclusive prefix (status P), leaves every
+// worker's (carry_in, offset) in gs->res[par] and returns true.
+// Position x <-> tile cur-1-x; lane i holds positions i, i+32, ... (word j of a mask = positions 32j .. 32j+31).
+template <int WG, int LB>
+__device__ __forceinline__ bool fz_chain_poll(const SweepArgs &a, FusedShared *gs, unsigned long long *desc, const FzPending &pd,
+                                              uint32_t n_tiles, int lane) {
+    const uint32_t cur = pd.cur;
+    unsigned long long d[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+        const long long idx = (long long)cur - 1 - lane - 32 * j;
+        d[j] = FZ_P;  // in front of tile 0: carry 0, nothing emitted
+        if (idx >= 0) d[j] = ld_desc(desc + idx);
+    }
+    int qw = -1, qb = 0;  // word and bit of the nearest inclusive prefix
+    bool hole = false;    // a tile nearer than it has published nothing yet
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+        const uint32_t st = uint32_t(d[j] >> 62);
+        const uint32_t pmj = __ballot_sync(FULL, st == 2u);
+        const uint32_t zmj = __ballot_sync(FULL, st == 0u);
+        if (qw < 0) {
+            if (pmj != 0u) {
+                qw = j;
+                qb = __ffs(pmj) - 1;
+                if (zmj & ((1u << qb) - 1u)) hole = true;
+            } else if (zmj != 0u) {
+                hole = true;
             }
-            if (++polls == (1u << 22)) {  // seconds: a predecessor died; fail the launch instead of hanging
-                *a.scratch.overflow = 3u;
-                break;
-            }
-            __nanosleep(64);
         }
     }
-    if (starts) c_in = 0;
-    const uint32_t c_out = tf.id ? c_in : tf.cst;
-    const unsigned long long total = base + tf.cnt0 - ((c_in && tf.delta) ? 1ull : 0ull);
+    if (qw < 0 || hole) return false;
+    const int q = 32 * qw + qb;
+    // The carry leaving position x: P.carry at q, the constant of a non-identity tile, else whatever enters it.
+    // nim = "non-identity" (with q itself), cm = that carry.  up_c[j]: the carry of the nearest non-identity position
+    // in words >= j (warp-uniform, filled from the far end).
+    uint32_t nim[LB], cm[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+        nim[j] = __ballot_sync(FULL, (d[j] & FZ_A_ID) == 0ull);
+        cm[j] = __ballot_sync(FULL, (d[j] & FZ_A_CST) != 0ull);
+        if (j > qw) nim[j] = 0u;
+        if (j == qw) nim[j] = (nim[j] & ((1u << qb) - 1u)) | (1u << qb);
+    }
+    uint32_t up_c[LB + 1];
+    up_c[LB] = 0u;
+#pragma unroll
+    for (int j = LB - 1; j >= 0; --j) {
+        up_c[j] = up_c[j + 1];
+        if (nim[j] != 0u) up_c[j] = (cm[j] >> (__ffs(nim[j]) - 1)) & 1u;
+    }
+    uint32_t e = 0;
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+        // the carry entering position 32j + lane leaves the nearest non-identity position behind it
+        const uint32_t above = (lane < 31) ? (nim[j] >> (lane + 1)) : 0u;
+        const uint32_t cin = above ? ((cm[j] >> (lane + __ffs(above))) & 1u) : up_c[j + 1];
+        if (32 * j + lane < q) e += uint32_t(d[j] & 0xffffffffull) - (((d[j] & FZ_A_DELTA) && cin) ? 1u : 0u);
+    }
+    e = __reduce_add_sync(FULL, e);
+    unsigned long long pdesc = 0;
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+        const unsigned long long v = __shfl_sync(FULL, d[j], qb);
+        if (j == qw) pdesc = v;
+    }
+    const unsigned long long base = (pdesc & FZ_COUNT) + e;
+    const uint32_t c_in = pd.starts ? 0u : up_c[0];  // the nearest non-identity position's carry enters this tile
+    const uint32_t c_out = pd.tf.id ? c_in : pd.tf.cst;
+    const unsigned long long total = base + pd.tf.cnt0 - ((c_in && pd.tf.delta) ? 1ull : 0ull);
     if (lane == 0) {
         st_desc(desc + cur, FZ_P | (c_out ? FZ_P_CARRY : 0ull) | total);
         if (cur == n_tiles - 1) {
@@ -297,16 +331,29 @@ __device__ __forceinline__ void fz_chain_tile(const SweepArgs &a, FusedShared *g
     }
     if (lane < WG) {
         // (the scan ran on the worker functions as they are: a chunk start only fixes the carry entering worker 0)
-        const uint32_t cw = ex.id ? c_in : ex.cst;
-        const unsigned long long bw = base + ex.cnt0 - ((c_in && ex.delta) ? 1ull : 0ull);
-        gs->res[par][lane] = (cw ? R_CARRY : 0ull) | bw;
+        const uint32_t cw = pd.ex.id ? c_in : pd.ex.cst;
+        const unsigned long long bw = base + pd.ex.cnt0 - ((c_in && pd.ex.delta) ? 1ull : 0ull);
+        gs->res[pd.par][lane] = (cw ? R_CARRY : 0ull) | bw;
     }
+    return true;
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0u;
 }
 
 template <int WG, int R>
 __global__ void __launch_bounds__((WG + 1) * 32, 1)
 fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsigned long long *__restrict__ desc,
-                   uint32_t *__restrict__ tile_counter, uint32_t n_tiles, unsigned long long chunk) {
+                   uint32_t n_tiles, unsigned long long chunk) {
     using C = FusedCfg<WG, R>;
     extern __shared__ __align__(16) unsigned char smem[];
     {  // the table, by everybody
@@ -318,63 +365,70 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     const int warp = threadIdx.x >> 5;
     const uint32_t smem_s = smem_u32(smem);
     const uint32_t tbl_s = smem_s;
-    const uint32_t stage0_s = (smem_s + C::OFF_STAGE + 1023u) & ~1023u;  // 1 KiB-aligned staging lines
+    const uint32_t stage0_s = (smem_s + C::OFF_STAGE + 127u) & ~127u;  // 128-byte aligned staging lines
     FusedShared *gs = reinterpret_cast<FusedShared *>(smem + C::OFF_GS);
     unsigned char *buf = smem + C::OFF_BUF;
-    const uint32_t bar = smem_u32(&gs->mbar);
+    const uint32_t bar_counted = smem_u32(&gs->counted[0]), bar_resolved = smem_u32(&gs->resolved[0]);
 
-    // ---- prologue: barrier, the first ticket and its copy ----------------------------------------------------
-    uint32_t t_next = 0xffffffffu;  // chain lane 0: the ticket of the next iteration
+    // ---- prologue: barriers, the geometry of the first two tiles -----------------------------------------------
+    // Tiles are dealt round-robin: iteration i of this CTA is tile blockIdx.x + i * gridDim.x (every worker can
+    // start the copy of its next slice without asking anybody).
+    const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
     if (warp == WG) {
         if (lane == 0) {
-            mbar_init(bar, 1);
+            for (int w = 0; w < WG; ++w) mbar_init(smem_u32(&gs->wbar[w]), 1);
+            mbar_init(bar_counted, WG);
+            mbar_init(bar_counted + 8, WG);
+            mbar_init(bar_resolved, 1);
+            mbar_init(bar_resolved + 8, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fz_tile_geometry<C>(a, chunk, tile0, n_tiles, gs, 0);
+            fz_tile_geometry<C>(a, chunk, (unsigned long long)tile0 + tile_step, n_tiles, gs, 1);
         }
-        __syncwarp();
-        uint32_t first = 0;
-        if (lane == 0) {
-            first = atomicAdd(tile_counter, 1u);
-            gs->tile[0] = first;
-            fz_tile_geometry<C>(a, chunk, first, n_tiles, gs, 0);
-            if (first < n_tiles) fz_issue_copy<C>(a, first, buf, bar);
-            t_next = (first < n_tiles) ? atomicAdd(tile_counter, 1u) : first;
-            gs->tile[1] = t_next;
-            fz_tile_geometry<C>(a, chunk, t_next, n_tiles, gs, 1);
-        }
-        first = __shfl_sync(FULL, first, 0);
-        if (first < n_tiles) fz_copy_tail<C>(a, first, buf, lane);
     }
-    __syncthreads();  // table, barrier, first tickets
+    __syncthreads();  // table, barriers, first geometry: the only CTA-wide barrier of the kernel
 
     if (warp == WG) {
         // =========================== chain warp ===========================
-        uint32_t cur = gs->tile[0], flags = gs->flags[0];
-        t_next = __shfl_sync(FULL, t_next, 0);
-        bool prev_new = false;
-        for (uint32_t it = 0;; ++it) {
-            const uint32_t par = it & 1u;
-            const bool have_new = cur < n_tiles;
-            if (!have_new && !prev_new) break;  // (the workers leave on the same condition: equal barrier counts)
-            cta_bar(C::THREADS);  // the workers have counted `cur`; they emit the tile before it now
-            prev_new = have_new;
-            if (!have_new) continue;
-            // the buffer is free: the next tile may land in it (ragged tail first: the barrier's arrive releases it)
-            if (t_next < n_tiles) {
-                fz_copy_tail<C>(a, t_next, buf, lane);
+        // Two duties that must not block each other: publishing the function of a tile as soon as its workers have
+        // counted it (other CTAs' look-backs wait for it), and resolving the tiles published before.  At most two
+        // tiles are pending: the workers cannot count tile i+1 before they have emitted tile i-1.
+        FzPending pend[2];
+        pend[0].cur = pend[1].cur = 0;
+        uint32_t n_pend = 0;            // pend[0] is the older one
+        unsigned long long nxt = tile0;  // the next tile of this CTA to be counted
+        uint32_t it = 0;                 // its iteration
+        uint32_t idle = 0;
+        while (nxt < n_tiles || n_pend != 0) {
+            bool progress = false;
+            if (nxt < n_tiles && n_pend < 2 && mbar_test(bar_counted + 8 * (it & 1u), (it >> 1) & 1u)) {
+                // every worker has counted tile `nxt`: its functions are in gs->fn_*[it & 1]
+                const FzPending p = fz_chain_publish<WG>(gs, desc, uint32_t(nxt), gs->flags[it & 1u], it & 1u, lane);
+                if (n_pend == 0) pend[0] = p; else pend[1] = p;
+                ++n_pend;
+                nxt += tile_step;
+                ++it;
+                progress = true;
+            }
+            if (n_pend != 0 && fz_chain_poll<WG, C::LB>(a, gs, desc, pend[0], n_tiles, lane)) {
+                const uint32_t par = pend[0].par;
+                // the geometry of the tile two iterations on goes into this tile's slot (its readers are done with it)
+                if (lane == 0) fz_tile_geometry<C>(a, chunk, (unsigned long long)pend[0].cur + 2ull * tile_step, n_tiles, gs, par);
                 __syncwarp();
-                if (lane == 0) fz_issue_copy<C>(a, t_next, buf, bar);
+                if (lane == 0) mbar_arrive(bar_resolved + 8 * par);  // releases res[par] and the slot written above
+                pend[0] = pend[1];
+                --n_pend;
+                progress = true;
             }
-            fz_chain_tile<WG>(a, gs, desc, cur, flags, par, n_tiles, lane);
-            // ticket of the iteration after the next one, published before the next barrier
-            cur = t_next;
-            flags = gs->flags[par ^ 1u];
-            uint32_t t2 = cur;
-            if (lane == 0) {
-                if (cur < n_tiles) t2 = atomicAdd(tile_counter, 1u);
-                gs->tile[par] = t2;
-                fz_tile_geometry<C>(a, chunk, t2, n_tiles, gs, par);
+            if (!progress) {
+                if (++idle == (1u << 24)) {  // seconds: somebody died; fail the launch instead of hanging
+                    *a.scratch.overflow = 3u;
+                    break;
+                }
+                __nanosleep(32);
+            } else {
+                idle = 0;
             }
-            t_next = __shfl_sync(FULL, t2, 0);
         }
         return;
     }
@@ -383,10 +437,11 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     const int wg = warp;
     const uint32_t stage_s = stage0_s + uint32_t(wg) * C::STAGE_BYTES;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t lane4 = uint32_t(lane) << 2;
-    const unsigned char *slice = buf + wg * C::WARP_BYTES;
+    unsigned char *slice = buf + wg * C::WBUF;  // this worker's slice of the tile being counted
+    const uint32_t wbar = smem_u32(&gs->wbar[wg]);
     const uint32_t slice_off = uint32_t(wg * C::WARP_BYTES);
     uint32_t parity = 0;
+    if (tile0 < n_tiles) fz_warp_copy<C>(a, tile0, wg, slice, wbar, lane);
     // the tile counted in the previous iteration: tokens and emit masks stay in registers until its prefix is known
     uint32_t hvP[R][4], ovP[R][4], emP[R];
     bool prev_valid = false, prev_full = true;
@@ -399,9 +454,9 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         for (int q = 0; q < 4; ++q) { hvP[k][q] = 0; ovP[k][q] = 0; }
     }
 
-    for (uint32_t it = 0;; ++it) {
+    unsigned long long cur = tile0;  // (64-bit: the tile after the last one may not fit 32 bits)
+    for (uint32_t it = 0;; ++it, cur += tile_step) {
         const uint32_t par = it & 1u;
-        const uint32_t cur = gs->tile[par];
         const bool have_new = cur < n_tiles;
         if (!have_new && !prev_valid) break;
         uint32_t hvN[R][4], ovN[R][4], emN[R];
@@ -410,14 +465,15 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         const unsigned long long wall_ck0 = gs->wall_ck[par][0], wall_ck1 = gs->wall_ck[par][1];
         const bool full = tile_len == uint32_t(C::TILE);
         if (have_new) {
-            if (!mbar_wait(bar, parity)) *a.scratch.overflow = 3u;
+            if (!mbar_wait(wbar, parity)) *a.scratch.overflow = 3u;
             parity ^= 1u;
             // ---- count: lookups (retained), run parity under carry_in = 0, the slice's carry function ----
             bool t_id = true;
             uint32_t t_const = 0, delta = 0, cnt0 = 0;
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const uint32_t off = slice_off + uint32_t(k * 512 + lane * 16);  // offset of the lane's segment in the tile
+                const uint32_t round_off = slice_off + uint32_t(k * 512);
+                const uint32_t off = round_off + uint32_t(lane * 16);  // offset of the lane's segment in the tile
                 const uint4 w = *reinterpret_cast<const uint4 *>(slice + k * 512 + lane * 16);
                 uint32_t next = __shfl_down_sync(FULL, w.x & 0xffu, 1);
                 if (lane == 31) next = slice[k * 512 + 512];
@@ -425,7 +481,6 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 fz_lookup<1>(tbl_s, w, next, ovN[k]);
                 uint32_t valid = 0xFFFFu;
                 if (!full) valid = (off + 16 <= tile_len) ? 0xFFFFu : (off < tile_len ? ((1u << (tile_len - off)) - 1u) : 0u);
-                const uint32_t round_off = slice_off + uint32_t(k * 512);
                 if (wall0 - round_off < 512u || wall1 - round_off < 512u) {  // warp-uniform: a wall is in this round
                     // a wall suppresses the pair that starts at the chunk's last element: the raw token goes out there
                     const uint32_t dj0 = wall0 - off, dj1 = wall1 - off;  // >= 16 (or wrapped) in every segment but one
@@ -461,136 +516,131 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     t_const = (cob >> (31 - __clz(nid))) & 1u;
                 }
             }
+            // every lane has read its share of the buffer: the slice of the next tile may land in it
+            if (cur + tile_step < n_tiles) fz_warp_copy<C>(a, uint32_t(cur + tile_step), wg, slice, wbar, lane);
+            else __syncwarp();
             if (lane == 0) {
                 gs->fn_flags[par][wg] = (t_id ? 1u : 0u) | (t_const << 1) | (delta << 2);
                 gs->fn_cnt[par][wg] = cnt0;
+                mbar_arrive(bar_counted + 8 * par);  // hands the slice's function to the chain warp
             }
         }
-        cta_bar(C::THREADS);  // hands the tile to the chain warp; the previous tile's prefix is in gs->res[par ^ 1]
 
-        // ---- emit (one tile behind): compaction of the retained tokens, streamed out in whole words -------------
+        // ---- emit (one tile behind): compaction of the retained tokens of the whole slice, streamed out in words ----
         if (prev_valid) {
-            const unsigned long long rv = gs->res[par ^ 1u][wg];
+            const uint32_t pp = par ^ 1u;
+            if (!mbar_wait(bar_resolved + 8 * pp, ((it - 1) >> 1) & 1u)) *a.scratch.overflow = 3u;
+            const unsigned long long rv = gs->res[pp][wg];
             const uint32_t slice_carry = uint32_t(rv >> 63);
-            const unsigned long long abs0 = (rv & ~R_CARRY) + a.out_base_tokens;
-            // stage[0 .. pend) holds tokens not yet written; logical token 0 of the line corresponds to a.out[wpos],
-            // wpos is even.  `head`: that slot belongs to the slice in front of this one and is not written here.
-            unsigned long long wpos = abs0 & ~1ull;
-            uint32_t pend = uint32_t(abs0 & 1ull);
-            uint32_t head = pend;
-            unsigned long long rel = rv & ~R_CARRY;  // tokens of the launch in front of the next round
-            bool dep = slice_carry != 0u;  // the lanes in front of the slice's first non-identity segment see carry_in = 1
-            auto flush = [&](uint32_t total) {
-                const uint32_t have = pend + total;
-                const uint32_t nw = have >> 1;
-                const bool fits = (wpos + have <= a.out_cap_tokens);
-                if (!fits && lane == 0) *a.scratch.overflow = 1u;
-                if (fits && nw != 0) {
-                    unsigned char *gout = reinterpret_cast<unsigned char *>(a.out + wpos) + lane4;
-                    {  // word v = lane + 32 i lives in window i of the line, XORed with i & 7
-                        const uint32_t word = lds_u32(stage_s + lane4);
-                        if (uint32_t(lane) < nw) {
-                            if (lane == 0 && head != 0) *reinterpret_cast<uint16_t *>(gout + 2) = uint16_t(word >> 16);
-                            else stg_stream_u32(gout, word);
-                        }
-                    }
+            const unsigned long long rel0 = rv & ~R_CARRY;  // tokens of the launch in front of the slice
+            const unsigned long long abs0 = rel0 + a.out_base_tokens;
+            // logical token 0 of the staging line corresponds to a.out[wpos], wpos is even; `head`: that slot belongs
+            // to the slice in front of this one (it holds nothing and is not written here)
+            const unsigned long long wpos = abs0 & ~1ull;
+            const uint32_t head = uint32_t(abs0 & 1ull);
+            if (slice_carry != 0u) {
+                // the lanes in front of the slice's first non-identity segment see carry_in = 1 (the count assumed 0)
+                bool dep = true;
 #pragma unroll
-                    for (int i = 1; i < 8; ++i) {
-                        if (uint32_t(32 * i) < nw) {  // warp-uniform
-                            const uint32_t word = lds_u32(stage_s + 128u * i + (lane4 ^ uint32_t((i & 7) << 2)));
-                            if (uint32_t(lane + 32 * i) < nw) stg_stream_u32(gout + 128 * i, word);
+                for (int k = 0; k < R; ++k) {
+                    if (dep) {  // warp-uniform
+                        const uint32_t off = slice_off + uint32_t(k * 512 + lane * 16);
+                        uint32_t valid = 0xFFFFu;
+                        if (!prev_full) valid = (off + 16 <= prev_len) ? 0xFFFFu : (off < prev_len ? ((1u << (prev_len - off)) - 1u) : 0u);
+                        const uint32_t m = fz_membership(hvP[k], ovP[k]) & valid;
+                        const uint32_t nid = ~__ballot_sync(FULL, m == 0xFFFFu);
+                        if ((nid & lt_mask) == 0u) {
+                            const uint32_t st1 = start_bits(m, 1u);
+                            emP[k] = valid & ~((st1 << 1) | 1u);
                         }
+                        if (nid) dep = false;
                     }
                 }
-                uint32_t keep = 0;
-                const bool odd = (have & 1u) != 0;
-                if (nw != 0 && odd && lane == 0)
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(keep) : "r"(stage_swz(stage_s + 2u * (have - 1u))) : "memory");
-                __syncwarp();
-                if (nw != 0) {
-                    if (odd && lane == 0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_s), "h"(uint16_t(keep)) : "memory");
-                    head = 0;
-                    wpos += 2ull * nw;
-                    pend = have & 1u;
-                } else {
-                    pend = have;
-                }
-                __syncwarp();
-            };
+            }
+            // token counts of all rounds at once: two rounds per scanned word
+            uint32_t pk[R / 2];
 #pragma unroll
-            for (int k = 0; k < R; ++k) {
-                uint32_t em = emP[k];
-                if (dep) {  // warp-uniform; false for good after the slice's first non-identity segment
+            for (int h = 0; h < R / 2; ++h) pk[h] = __popc(emP[2 * h]) | (__popc(emP[2 * h + 1]) << 16);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                for (int h = 0; h < R / 2; ++h) {
+                    const uint32_t tq = __shfl_up_sync(FULL, pk[h], d);
+                    if (lane >= d) pk[h] += tq;
+                }
+            }
+            uint32_t pos[R];  // tokens of the slice in front of the lane's segment of round k
+            uint32_t have = 0;  // tokens of the slice
+#pragma unroll
+            for (int h = 0; h < R / 2; ++h) {
+                const uint32_t tot = __shfl_sync(FULL, pk[h], 31);
+                pos[2 * h] = have + (pk[h] & 0xffffu) - __popc(emP[2 * h]);
+                have += tot & 0xffffu;
+                pos[2 * h + 1] = have + (pk[h] >> 16) - __popc(emP[2 * h + 1]);
+                have += tot >> 16;
+            }
+            if (a.chunk_ends != nullptr) {  // chunks that end in this slice: their output ends behind the wall's token
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
                     const uint32_t off = slice_off + uint32_t(k * 512 + lane * 16);
-                    uint32_t valid = 0xFFFFu;
-                    if (!prev_full) valid = (off + 16 <= prev_len) ? 0xFFFFu : (off < prev_len ? ((1u << (prev_len - off)) - 1u) : 0u);
-                    const uint32_t m = fz_membership(hvP[k], ovP[k]) & valid;
-                    const uint32_t nid = ~__ballot_sync(FULL, m == 0xFFFFu);
-                    if ((nid & lt_mask) == 0u) {
-                        const uint32_t st1 = start_bits(m, 1u);
-                        em = valid & ~((st1 << 1) | 1u);
-                    }
-                    if (nid) dep = false;
+                    const uint32_t dj0 = prev_wall0 - off, dj1 = prev_wall1 - off;  // 0 .. 15 in the wall's lane only
+                    if (dj0 < 16u) a.chunk_ends[prev_wall_ck0] = a.chunk_ends_base + 2ull * (rel0 + pos[k] + __popc(emP[k] & ((2u << dj0) - 1u)));
+                    if (dj1 < 16u) a.chunk_ends[prev_wall_ck1] = a.chunk_ends_base + 2ull * (rel0 + pos[k] + __popc(emP[k] & ((2u << dj1) - 1u)));
                 }
-                // a chunk that ends in this round: its output ends behind the token of the wall position
-                const uint32_t round_off = slice_off + uint32_t(k * 512);
-                const bool wall_here = (prev_wall0 - round_off < 512u || prev_wall1 - round_off < 512u) && a.chunk_ends != nullptr;  // warp-uniform
-                const uint32_t dj0 = prev_wall0 - (round_off + uint32_t(lane * 16)), dj1 = prev_wall1 - (round_off + uint32_t(lane * 16));
-                const uint32_t x = em ^ 0x5555u;
-                const bool dense0 = __all_sync(FULL, x == 0u), dense1 = __all_sync(FULL, x == 0xFFFFu);
-                if ((dense0 || dense1) && pend == 0 && (wpos & 7ull) == 0) {
-                    // every lane emits exactly the 8 tokens of one parity and the output is vector-aligned
-                    const uint32_t *tv = dense0 ? hvP[k] : ovP[k];
-                    if (wpos + 256 <= a.out_cap_tokens) stg_stream_v4(a.out + wpos + size_t(lane) * 8, make_uint4(tv[0], tv[1], tv[2], tv[3]));
-                    else if (lane == 0) *a.scratch.overflow = 1u;
-                    if (wall_here) {
-                        if (dj0 < 16u) a.chunk_ends[prev_wall_ck0] = a.chunk_ends_base + 2ull * (rel + 8u * lane + __popc(em & ((2u << dj0) - 1u)));
-                        if (dj1 < 16u) a.chunk_ends[prev_wall_ck1] = a.chunk_ends_base + 2ull * (rel + 8u * lane + __popc(em & ((2u << dj1) - 1u)));
-                    }
-                    wpos += 256;
-                    rel += 256;
-                    head = 0;
-                    continue;
-                }
-                const uint32_t cnt = __popc(em);
-                uint32_t incl = cnt;
+            }
+            const bool fits = (abs0 + have <= a.out_cap_tokens);
+            if (!fits && lane == 0) *a.scratch.overflow = 1u;
+            // dense slice: every lane emits exactly the 8 tokens of one parity in every round
+            uint32_t x_or = 0, x_and = 0xFFFFu;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t tq = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl += tq;
+            for (int k = 0; k < R; ++k) { x_or |= emP[k] ^ 0x5555u; x_and &= emP[k] ^ 0x5555u; }
+            const bool dense0 = __all_sync(FULL, x_or == 0u), dense1 = __all_sync(FULL, x_and == 0xFFFFu);
+            if (fits && (dense0 || dense1) && (abs0 & 7ull) == 0) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const uint32_t *tv = dense0 ? hvP[k] : ovP[k];
+                    stg_stream_v4(a.out + abs0 + size_t(k) * 256 + size_t(lane) * 8, make_uint4(tv[0], tv[1], tv[2], tv[3]));
                 }
-                const uint32_t total = __shfl_sync(FULL, incl, 31);
-                if (wall_here) {
-                    if (dj0 < 16u) a.chunk_ends[prev_wall_ck0] = a.chunk_ends_base + 2ull * (rel + (incl - cnt) + __popc(em & ((2u << dj0) - 1u)));
-                    if (dj1 < 16u) a.chunk_ends[prev_wall_ck1] = a.chunk_ends_base + 2ull * (rel + (incl - cnt) + __popc(em & ((2u << dj1) - 1u)));
-                }
-                rel += total;
-                uint32_t sp = stage_s + 2u * (pend + incl - cnt);  // where the lane's next token goes (before swizzling)
+            } else if (fits) {
+                // R independent chains of predicated 2-byte stores (position-major so that they interleave)
+                uint32_t sp[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) sp[k] = stage_s + 2u * (head + pos[k]);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const uint32_t v = (j & 1) ? ovP[k][j >> 2] : hvP[k][j >> 2];
-                    const uint32_t tok = ((j >> 1) & 1) ? (v >> 16) : v;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                        "setp.ne.u32 p, %2, 0;\n\t"
-                        "shr.u32 t, %0, 5;\n\t"
-                        "and.b32 t, t, 0x1C;\n\t"
-                        "xor.b32 t, t, %0;\n\t"
-                        "@p st.shared.u16 [t], %1;\n\t"
-                        "@p add.u32 %0, %0, 2;\n\t}"
-                        : "+r"(sp)
-                        : "h"(uint16_t(tok)), "r"(em & (1u << j))
-                        : "memory");
+#pragma unroll
+                    for (int k = 0; k < R; ++k) {
+                        const uint32_t v = (j & 1) ? ovP[k][j >> 2] : hvP[k][j >> 2];
+                        const uint32_t tok = ((j >> 1) & 1) ? (v >> 16) : v;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                            "setp.ne.u32 p, %2, 0;\n\t"
+                            "shr.u32 t, %0, 5;\n\t"
+                            "and.b32 t, t, 0x1C;\n\t"
+                            "xor.b32 t, t, %0;\n\t"
+                            "@p st.shared.u16 [t], %1;\n\t"
+                            "@p add.u32 %0, %0, 2;\n\t}"
+                            : "+r"(sp[k])
+                            : "h"(uint16_t(tok)), "r"(emP[k] & (1u << j))
+                            : "memory");
+                    }
                 }
                 __syncwarp();
-                flush(total);
-            }
-            // the slice's last odd token (the next slice starts right behind it)
-            if (pend > head && lane == 0) {
-                uint32_t last;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(last) : "r"(stage_s) : "memory");
-                if (wpos + 1 <= a.out_cap_tokens) a.out[wpos] = uint16_t(last);
-                else *a.scratch.overflow = 1u;
+                // tokens head .. total-1 of the line go to a.out[wpos + head ...]: whole words, then the odd last token
+                const uint32_t total = head + have;
+                const uint32_t nw = total >> 1;
+                unsigned char *gout = reinterpret_cast<unsigned char *>(a.out + wpos);
+                for (uint32_t v = lane; v < nw; v += 32) {
+                    const uint32_t word = lds_u32(stage_swz(stage_s + 4u * v));
+                    if (v == 0 && head != 0) *reinterpret_cast<uint16_t *>(gout + 2) = uint16_t(word >> 16);
+                    else stg_stream_u32(gout + 4u * v, word);
+                }
+                if ((total & 1u) && total - 1u >= head && total != 0u && lane == 0) {
+                    uint32_t last;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(last) : "r"(stage_swz(stage_s + 2u * (total - 1u))) : "memory");
+                    if (!(total == 1u && head == 1u)) *reinterpret_cast<uint16_t *>(gout + 2u * (total - 1u)) = uint16_t(last);
+                }
+                __syncwarp();
             }
         }
         // the tile just counted becomes the one to emit
@@ -644,9 +694,8 @@ struct FusedLaunch {
         size_t grid = tiles;
         if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
         const size_t chunk = (a.chunk == 0 || a.chunk > a.n) ? a.n : a.chunk;
-        uint32_t *counter = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(a.scratch.ctrl) + 320);
         fused_sweep_kernel<WG, R><<<dim3(unsigned(grid)), dim3(C::THREADS), C::SMEM, stream>>>(
-            a, d_table, reinterpret_cast<unsigned long long *>(a.scratch.meta), counter, uint32_t(tiles), (unsigned long long)chunk);
+            a, d_table, reinterpret_cast<unsigned long long *>(a.scratch.meta), uint32_t(tiles), (unsigned long long)chunk);
         return cudaGetLastError();
     }
 };
