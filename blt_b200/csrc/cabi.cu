@@ -370,6 +370,13 @@ blt_strategy::~blt_strategy() {
     resident.release();
 }
 
+#ifdef BLT_FUSED_PROF
+namespace bltk { cudaError_t debug_fused_profile(unsigned long long *host_out, size_t n_words); }
+extern "C" __attribute__((visibility("default"))) int blt_debug_fused_profile(unsigned long long *out, size_t n_words) {
+    return bltk::debug_fused_profile(out, n_words) == cudaSuccess ? 0 : -5;
+}
+#endif
+
 using namespace bltc;
 
 extern "C" {

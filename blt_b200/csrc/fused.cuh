@@ -36,9 +36,23 @@ constexpr unsigned long long FZ_P_CARRY = 1ull << 60;  // same bit as FZ_A_CST: 
 constexpr unsigned long long FZ_COUNT = (1ull << 56) - 1;
 constexpr uint32_t FZ_F_START = 2u, FZ_NO_WALL = 0xffffffffu;
 
+// BLT_FUSED_PROF builds only: per worker (CTA x 16 + worker) x 8 counters, in clock cycles:
+// 0 waiting for the slice copy, 1 counting, 2 waiting for the chain warp, 3 emitting, 4 tiles, 5 SM id
+#ifdef BLT_FUSED_PROF
+__device__ unsigned long long g_fz_prof[256 * 16 * 8];
+#define FZ_PROF(stmt) stmt
+#else
+#define FZ_PROF(stmt)
+#endif
+
 struct FusedShared {
     unsigned long long wbar[16];       // per worker: completion of the bulk copy of its slice
-    unsigned long long counted[2];     // every worker has counted the tile of iteration i (slot i & 1): WG arrivals
+    unsigned long long counted[2];     // the tile of iteration i (slot i & 1) is counted and its function published: one arrival
+    uint32_t arrived[2];               // workers that have counted it (the last one composes and publishes the function)
+    uint32_t tf_flags[2];              // the tile's function, left for the chain warp by that worker (+ bit3: starts a chunk)
+    unsigned long long tf_cnt[2];
+    uint32_t ex_flags[2][16];          // per worker: the workers in front of it composed
+    unsigned long long ex_cnt[2][16];
     unsigned long long resolved[2];    // the chain warp has left that tile's prefix in res[i & 1]: one arrival
     uint32_t flags[2];                 // FZ_F_START: it starts a chunk (the carry entering it is 0)
     uint32_t wall[2][2];               // offsets of the (at most two) chunk-last elements inside the tile, else FZ_NO_WALL:
@@ -65,8 +79,8 @@ struct FusedCfg {
     static constexpr int OFF_STAGE = PairsFE::TABLE_BYTES;  // + up to 128 bytes of alignment slack
     static constexpr int OFF_BUF = OFF_STAGE + WG * STAGE_BYTES + 128;
     static constexpr int OFF_GS = OFF_BUF + BUF;
-    static constexpr int SMEM = OFF_GS + 1024;
-    static_assert(sizeof(FusedShared) <= 1024, "control block");
+    static constexpr int SMEM = OFF_GS + 2048;
+    static_assert(sizeof(FusedShared) <= 2048, "control block");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -80,19 +94,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// false: the copy did not land within ~2 s (reported as a CUDA error by the host instead of hanging the device)
+// false: the phase did not complete within seconds (reported as a CUDA error by the host instead of hanging the device).
+// SLEEP: nanoseconds between two looks (a waiting warp must not eat the issue slots of the working ones).
+template <int SLEEP>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (int tries = 0; tries < 4096 && ok == 0u; ++tries) {
+    for (uint32_t tries = 0; tries < (1u << 24); ++tries) {
+        uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x80000;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(bar), "r"(parity)
             : "memory");
+        if (ok != 0u) return true;
+        __nanosleep(SLEEP);
     }
-    return ok != 0u;
+    return false;
 }
 // global -> shared bulk copy (the TMA unit's 1-D form): 16-byte aligned addresses, size a multiple of 16
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -130,17 +148,25 @@ __device__ __forceinline__ uint32_t stage_swz(uint32_t addr) { return addr ^ ((a
 
 // The SEG/2 pairs of one 16-byte segment that start at positions of parity PAR: the big-endian u16 to emit at each of
 // those positions (merged id if the pair is a rule, else the element itself), two per register in position order.
+// (Integer shifts and adds go to the alu pipe, which takes one warp instruction every two cycles per scheduler and is
+// this kernel's busiest unit; multiply-high by a power of two is a right shift on the fma pipe, multiply-add an address
+// computation there.)
+__device__ __forceinline__ uint32_t shr_fma(uint32_t x, uint32_t two_pow_32_minus_k) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(two_pow_32_minus_k));
+    return r;
+}
 template <int PAR>
 __device__ __forceinline__ void fz_lookup(uint32_t tbl_s, const uint4 &w, uint32_t next, uint32_t *vals) {
     const uint32_t W[4] = {PAR ? __funnelshift_r(w.x, w.y, 8) : w.x, PAR ? __funnelshift_r(w.y, w.z, 8) : w.y,
                            PAR ? __funnelshift_r(w.z, w.w, 8) : w.z, PAR ? __funnelshift_r(w.w, next, 8) : w.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t y = W[k] ^ ((W[k] >> 7) & 0x01FF01FFu);  // pair_table_index of both halves at once
+        const uint32_t y = W[k] ^ (shr_fma(W[k], 1u << 25) & 0x01FF01FFu);  // pair_table_index of both halves at once
         // entry address = table + 2 * index: one multiply-add per entry (the compiler's own form is shift, mask, add)
         uint32_t a0, a1;
         asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a0) : "r"(y & 0xFFFFu), "r"(tbl_s));
-        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a1) : "r"(y >> 16), "r"(tbl_s));
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a1) : "r"(shr_fma(y, 1u << 16)), "r"(tbl_s));
         vals[k] = __byte_perm(lds_tbl(a0), lds_tbl(a1), 0x5410);
     }
 }
@@ -182,19 +208,19 @@ __device__ __forceinline__ void fz_warp_copy(const SweepArgs &a, uint32_t t, int
 }
 
 // Where tile t meets chunk walls - chain lane 0.  Chunks are at least a tile long, so a tile holds at most one chunk
-// boundary; the input's last tile may hold the end of the input as well.
+// boundary; the input's last tile may hold the end of the input as well.  ck / rem: the chunk the tile starts in and
+// its offset in that chunk (tracked incrementally by the caller: no division per tile).
 template <class C>
 __device__ __forceinline__ void fz_tile_geometry(const SweepArgs &a, unsigned long long chunk, unsigned long long t, uint32_t n_tiles,
+                                                 unsigned long long ck, unsigned long long rem, unsigned long long last_ck,
                                                  FusedShared *gs, uint32_t slot) {
     uint32_t flags = 0, wall0 = FZ_NO_WALL, wall1 = FZ_NO_WALL, len = 0;
-    unsigned long long ck = 0;
     if (t < n_tiles) {
         const unsigned long long base = t * C::TILE;
         len = (a.n - base < (unsigned long long)C::TILE) ? uint32_t(a.n - base) : uint32_t(C::TILE);
-        ck = base / chunk;
-        if (base - ck * chunk == 0) flags |= FZ_F_START;
-        const unsigned long long last = (ck + 1) * chunk - 1;  // the last element of the chunk the tile starts in
-        if (last - base < (unsigned long long)len) wall0 = uint32_t(last - base);
+        if (rem == 0) flags |= FZ_F_START;
+        const unsigned long long to_last = chunk - 1 - rem;  // distance to the last element of the chunk the tile starts in
+        if (to_last < (unsigned long long)len) wall0 = uint32_t(to_last);
         if (t + 1 == n_tiles && wall0 != len - 1u) wall1 = len - 1u;  // the input's last element ends the last chunk
     }
     gs->flags[slot] = flags;
@@ -202,7 +228,7 @@ __device__ __forceinline__ void fz_tile_geometry(const SweepArgs &a, unsigned lo
     gs->wall[slot][0] = wall0;
     gs->wall[slot][1] = wall1;
     gs->wall_ck[slot][0] = ck;
-    gs->wall_ck[slot][1] = (a.n - 1) / chunk;
+    gs->wall_ck[slot][1] = last_ck;
 }
 
 // ---- the chain warp ------------------------------------------------------------------------------------------
@@ -377,13 +403,17 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     if (warp == WG) {
         if (lane == 0) {
             for (int w = 0; w < WG; ++w) mbar_init(smem_u32(&gs->wbar[w]), 1);
-            mbar_init(bar_counted, WG);
-            mbar_init(bar_counted + 8, WG);
+            mbar_init(bar_counted, 1);
+            mbar_init(bar_counted + 8, 1);
+            gs->arrived[0] = gs->arrived[1] = 0u;
             mbar_init(bar_resolved, 1);
             mbar_init(bar_resolved + 8, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            fz_tile_geometry<C>(a, chunk, tile0, n_tiles, gs, 0);
-            fz_tile_geometry<C>(a, chunk, (unsigned long long)tile0 + tile_step, n_tiles, gs, 1);
+            const unsigned long long last_ck = (a.n - 1) / chunk;
+            for (uint32_t j = 0; j < 2; ++j) {
+                const unsigned long long base = ((unsigned long long)tile0 + (unsigned long long)j * tile_step) * C::TILE;
+                fz_tile_geometry<C>(a, chunk, (unsigned long long)tile0 + (unsigned long long)j * tile_step, n_tiles, base / chunk, base % chunk, last_ck, gs, j);
+            }
         }
     }
     __syncthreads();  // table, barriers, first geometry: the only CTA-wide barrier of the kernel
@@ -393,6 +423,12 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         // Two duties that must not block each other: publishing the function of a tile as soon as its workers have
         // counted it (other CTAs' look-backs wait for it), and resolving the tiles published before.  At most two
         // tiles are pending: the workers cannot count tile i+1 before they have emitted tile i-1.
+        // geometry of the tile two iterations ahead, advanced without divisions
+        const unsigned long long last_ck = (a.n - 1) / chunk;
+        const unsigned long long step_bytes = (unsigned long long)tile_step * C::TILE;
+        const unsigned long long step_ck = step_bytes / chunk, step_rem = step_bytes % chunk;
+        unsigned long long g_ck = (((unsigned long long)tile0 + 2ull * tile_step) * C::TILE) / chunk;
+        unsigned long long g_rem = (((unsigned long long)tile0 + 2ull * tile_step) * C::TILE) % chunk;
         FzPending pend[2];
         pend[0].cur = pend[1].cur = 0;
         uint32_t n_pend = 0;            // pend[0] is the older one
@@ -402,8 +438,22 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         while (nxt < n_tiles || n_pend != 0) {
             bool progress = false;
             if (nxt < n_tiles && n_pend < 2 && mbar_test(bar_counted + 8 * (it & 1u), (it >> 1) & 1u)) {
-                // every worker has counted tile `nxt`: its functions are in gs->fn_*[it & 1]
-                const FzPending p = fz_chain_publish<WG>(gs, desc, uint32_t(nxt), gs->flags[it & 1u], it & 1u, lane);
+                // tile `nxt` is counted and its function published (by the last worker to finish): take it over
+                const uint32_t par = it & 1u;
+                FzPending p;
+                const uint32_t tfl = gs->tf_flags[par];
+                p.tf.id = tfl & 1u; p.tf.cst = (tfl >> 1) & 1u; p.tf.delta = (tfl >> 2) & 1u; p.starts = (tfl >> 3) & 1u;
+                p.tf.cnt0 = gs->tf_cnt[par];
+                const uint32_t efl = gs->ex_flags[par][lane & 15];
+                p.ex.id = efl & 1u; p.ex.cst = (efl >> 1) & 1u; p.ex.delta = (efl >> 2) & 1u;
+                p.ex.cnt0 = gs->ex_cnt[par][lane & 15];
+                p.cur = uint32_t(nxt); p.par = par;
+                // the geometry of the tile two iterations on goes into this tile's slot: every reader of the slot is done
+                // with it (the workers read it before they count); the `resolved` arrive below releases it
+                if (lane == 0) fz_tile_geometry<C>(a, chunk, nxt + 2ull * tile_step, n_tiles, g_ck, g_rem, last_ck, gs, par);
+                g_ck += step_ck;
+                g_rem += step_rem;
+                if (g_rem >= chunk) { g_rem -= chunk; ++g_ck; }
                 if (n_pend == 0) pend[0] = p; else pend[1] = p;
                 ++n_pend;
                 nxt += tile_step;
@@ -412,8 +462,6 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             }
             if (n_pend != 0 && fz_chain_poll<WG, C::LB>(a, gs, desc, pend[0], n_tiles, lane)) {
                 const uint32_t par = pend[0].par;
-                // the geometry of the tile two iterations on goes into this tile's slot (its readers are done with it)
-                if (lane == 0) fz_tile_geometry<C>(a, chunk, (unsigned long long)pend[0].cur + 2ull * tile_step, n_tiles, gs, par);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_resolved + 8 * par);  // releases res[par] and the slot written above
                 pend[0] = pend[1];
@@ -425,7 +473,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     *a.scratch.overflow = 3u;
                     break;
                 }
-                __nanosleep(32);
+                __nanosleep(20);
             } else {
                 idle = 0;
             }
@@ -455,6 +503,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     }
 
     unsigned long long cur = tile0;  // (64-bit: the tile after the last one may not fit 32 bits)
+    FZ_PROF(long long pf_copy = 0; long long pf_count = 0; long long pf_chain = 0; long long pf_emit = 0; long long pf_tiles = 0; long long pf_t = clock64();)
     for (uint32_t it = 0;; ++it, cur += tile_step) {
         const uint32_t par = it & 1u;
         const bool have_new = cur < n_tiles;
@@ -465,8 +514,10 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         const unsigned long long wall_ck0 = gs->wall_ck[par][0], wall_ck1 = gs->wall_ck[par][1];
         const bool full = tile_len == uint32_t(C::TILE);
         if (have_new) {
-            if (!mbar_wait(wbar, parity)) *a.scratch.overflow = 3u;
+            FZ_PROF(pf_t = clock64();)
+            if (!mbar_wait<20>(wbar, parity)) *a.scratch.overflow = 3u;
             parity ^= 1u;
+            FZ_PROF({ const long long t1 = clock64(); pf_copy += t1 - pf_t; pf_t = t1; ++pf_tiles; })
             // ---- count: lookups (retained), run parity under carry_in = 0, the slice's carry function ----
             bool t_id = true;
             uint32_t t_const = 0, delta = 0, cnt0 = 0;
@@ -519,17 +570,40 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             // every lane has read its share of the buffer: the slice of the next tile may land in it
             if (cur + tile_step < n_tiles) fz_warp_copy<C>(a, uint32_t(cur + tile_step), wg, slice, wbar, lane);
             else __syncwarp();
+            uint32_t last = 0;
             if (lane == 0) {
                 gs->fn_flags[par][wg] = (t_id ? 1u : 0u) | (t_const << 1) | (delta << 2);
                 gs->fn_cnt[par][wg] = cnt0;
-                mbar_arrive(bar_counted + 8 * par);  // hands the slice's function to the chain warp
+                __threadfence_block();
+                last = (atomicAdd(&gs->arrived[par], 1u) == uint32_t(WG - 1)) ? 1u : 0u;
             }
+            last = __shfl_sync(FULL, last, 0);
+            if (last) {
+                // the last worker to finish composes the WG functions and publishes the tile's function right away (no
+                // detour through the chain warp: other CTAs' look-backs are waiting for it), then hands the tile over
+                __threadfence_block();
+                if (lane == 0) gs->arrived[par] = 0u;
+                const FzPending p = fz_chain_publish<WG>(gs, desc, uint32_t(cur), gs->flags[par], par, lane);
+                if (lane < WG) {
+                    gs->ex_flags[par][lane] = p.ex.id | (p.ex.cst << 1) | (p.ex.delta << 2);
+                    gs->ex_cnt[par][lane] = p.ex.cnt0;
+                }
+                if (lane == 0) {
+                    gs->tf_flags[par] = p.tf.id | (p.tf.cst << 1) | (p.tf.delta << 2) | (p.starts << 3);
+                    gs->tf_cnt[par] = p.tf.cnt0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_counted + 8 * par);
+            }
+            FZ_PROF({ const long long t1 = clock64(); pf_count += t1 - pf_t; pf_t = t1; })
         }
 
         // ---- emit (one tile behind): compaction of the retained tokens of the whole slice, streamed out in words ----
         if (prev_valid) {
             const uint32_t pp = par ^ 1u;
-            if (!mbar_wait(bar_resolved + 8 * pp, ((it - 1) >> 1) & 1u)) *a.scratch.overflow = 3u;
+            FZ_PROF(pf_t = clock64();)
+            if (!mbar_wait<100>(bar_resolved + 8 * pp, ((it - 1) >> 1) & 1u)) *a.scratch.overflow = 3u;
+            FZ_PROF({ const long long t1 = clock64(); pf_chain += t1 - pf_t; pf_t = t1; })
             const unsigned long long rv = gs->res[pp][wg];
             const uint32_t slice_carry = uint32_t(rv >> 63);
             const unsigned long long rel0 = rv & ~R_CARRY;  // tokens of the launch in front of the slice
@@ -615,11 +689,11 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                         asm volatile(
                             "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
                             "setp.ne.u32 p, %2, 0;\n\t"
-                            "shr.u32 t, %0, 5;\n\t"
+                            "mul.hi.u32 t, %0, 0x08000000;\n\t"
                             "and.b32 t, t, 0x1C;\n\t"
                             "xor.b32 t, t, %0;\n\t"
                             "@p st.shared.u16 [t], %1;\n\t"
-                            "@p add.u32 %0, %0, 2;\n\t}"
+                            "@p mad.lo.u32 %0, %0, 1, 2;\n\t}"
                             : "+r"(sp[k])
                             : "h"(uint16_t(tok)), "r"(emP[k] & (1u << j))
                             : "memory");
@@ -630,10 +704,18 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 const uint32_t total = head + have;
                 const uint32_t nw = total >> 1;
                 unsigned char *gout = reinterpret_cast<unsigned char *>(a.out + wpos);
-                for (uint32_t v = lane; v < nw; v += 32) {
-                    const uint32_t word = lds_u32(stage_swz(stage_s + 4u * v));
-                    if (v == 0 && head != 0) *reinterpret_cast<uint16_t *>(gout + 2) = uint16_t(word >> 16);
-                    else stg_stream_u32(gout + 4u * v, word);
+                // word v = lane + 32 i sits in window i of the line: its bank bits are XORed with (window index) & 7
+                const uint32_t lane4 = uint32_t(lane) << 2;
+                const uint32_t w7 = stage_s >> 7;
+                if (uint32_t(lane) < nw) {
+                    const uint32_t word = lds_u32(stage_s + (lane4 ^ ((w7 & 7u) << 2)));
+                    if (lane == 0 && head != 0) *reinterpret_cast<uint16_t *>(gout + 2) = uint16_t(word >> 16);
+                    else stg_stream_u32(gout + lane4, word);
+                }
+#pragma unroll 4
+                for (uint32_t i = 1; i * 32u < nw; ++i) {  // warp-uniform trip count
+                    const uint32_t word = lds_u32(stage_s + i * 128u + (lane4 ^ (((w7 + i) & 7u) << 2)));
+                    if (i * 32u + uint32_t(lane) < nw) stg_stream_u32(gout + i * 128u + lane4, word);
                 }
                 if ((total & 1u) && total - 1u >= head && total != 0u && lane == 0) {
                     uint32_t last;
@@ -643,6 +725,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 __syncwarp();
             }
         }
+        FZ_PROF(if (prev_valid) { const long long t1 = clock64(); pf_emit += t1 - pf_t; pf_t = t1; })
         // the tile just counted becomes the one to emit
         prev_valid = have_new;
         prev_full = full;
@@ -658,6 +741,12 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             for (int q = 0; q < 4; ++q) { hvP[k][q] = hvN[k][q]; ovP[k][q] = ovN[k][q]; }
         }
     }
+    FZ_PROF(if (lane == 0 && blockIdx.x < 256) {
+        unsigned long long *pp = g_fz_prof + (size_t(blockIdx.x) * 16 + wg) * 8;
+        uint32_t smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        pp[0] = pf_copy; pp[1] = pf_count; pp[2] = pf_chain; pp[3] = pf_emit; pp[4] = pf_tiles; pp[5] = smid;
+    })
 }
 
 template <int WG, int R>

@@ -479,6 +479,12 @@ cudaError_t launch_pair_hist(const unsigned char *d_in, size_t n, unsigned long 
 
 cudaError_t launch_detokenize(const DetokArgs &a, cudaStream_t stream) { return launch_detok_impl(a, stream); }
 
+#ifdef BLT_FUSED_PROF
+cudaError_t debug_fused_profile(unsigned long long *host_out, size_t n_words) {
+    return cudaMemcpyFromSymbol(host_out, g_fz_prof, n_words * 8, 0, cudaMemcpyDeviceToHost);
+}
+#endif
+
 // ---- scratch -------------------------------------------------------------------------------------
 size_t sweep_scratch_bytes(size_t n_elems_max) {
     const size_t tiles = 2 * 8192;
