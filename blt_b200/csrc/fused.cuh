@@ -45,27 +45,33 @@ __device__ unsigned long long g_fz_prof[256 * 16 * 8];
 #define FZ_PROF(stmt)
 #endif
 
+constexpr int FZ_DMAX = 4;  // deepest pipeline: tiles a worker holds between "counted" and "emitted"
+
 struct FusedShared {
-    unsigned long long wbar[16];       // per worker: completion of the bulk copy of its slice
-    unsigned long long counted[2];     // the tile of iteration i (slot i & 1) is counted and its function published: one arrival
-    uint32_t arrived[2];               // workers that have counted it (the last one composes and publishes the function)
-    uint32_t tf_flags[2];              // the tile's function, left for the chain warp by that worker (+ bit3: starts a chunk)
-    unsigned long long tf_cnt[2];
-    uint32_t ex_flags[2][16];          // per worker: the workers in front of it composed
-    unsigned long long ex_cnt[2][16];
-    unsigned long long resolved[2];    // the chain warp has left that tile's prefix in res[i & 1]: one arrival
-    uint32_t flags[2];                 // FZ_F_START: it starts a chunk (the carry entering it is 0)
-    uint32_t wall[2][2];               // offsets of the (at most two) chunk-last elements inside the tile, else FZ_NO_WALL:
-                                       //   [0] a chunk boundary, [1] the end of the input if it is another element
-    uint32_t len[2];                   // valid bytes of the tile (the tile size but for the input's last tile)
-    unsigned long long wall_ck[2][2];  // the chunks those walls end
-    unsigned long long fn_cnt[2][16];  // per worker: tokens of its slice for carry_in 0
-    uint32_t fn_flags[2][16];          // per worker: bit0 identity, bit1 constant carry_out, bit2 delta
-    unsigned long long res[2][16];     // per worker: carry_in << 63 | tokens of the launch in front of its slice
+    unsigned long long wbar[16];              // per worker: completion of the bulk copy of its slice
+    // per tile in flight, slot = iteration % D:
+    unsigned long long counted[FZ_DMAX];      // the tile is counted and its function published: one arrival
+    unsigned long long resolved[FZ_DMAX];     // the chain warp has left that tile's prefix in res[slot]: one arrival
+    uint32_t arrived[FZ_DMAX];                // workers that have counted it (the last one composes and publishes the function)
+    uint32_t tf_flags[FZ_DMAX];               // the tile's function, left for the chain warp by that worker (+ bit3: starts a chunk)
+    unsigned long long tf_cnt[FZ_DMAX];
+    uint32_t ex_flags[FZ_DMAX][16];           // per worker: the workers in front of it composed
+    unsigned long long ex_cnt[FZ_DMAX][16];
+    unsigned long long fn_cnt[FZ_DMAX][16];   // per worker: tokens of its slice for carry_in 0
+    uint32_t fn_flags[FZ_DMAX][16];           // per worker: bit0 identity, bit1 constant carry_out, bit2 delta
+    unsigned long long res[FZ_DMAX][16];      // per worker: carry_in << 63 | tokens of the launch in front of its slice
+    // geometry, slot = iteration % (2 D): written D iterations ahead, read when the tile is counted and when it is emitted
+    uint32_t flags[2 * FZ_DMAX];              // FZ_F_START: it starts a chunk (the carry entering it is 0)
+    uint32_t len[2 * FZ_DMAX];                // valid bytes of the tile (the tile size but for the input's last tile)
+    uint32_t wall[2 * FZ_DMAX][2];            // offsets of the (at most two) chunk-last elements inside the tile, else FZ_NO_WALL:
+                                              //   [0] a chunk boundary, [1] the end of the input if it is another element
+    unsigned long long wall_ck[2 * FZ_DMAX][2];  // the chunks those walls end
+    FZ_PROF(long long t_first[FZ_DMAX]; long long t_pub[FZ_DMAX];)  // first / last worker done with the tile (clock64)
 };
 
-template <int WG, int R>
+template <int WG, int R, int D>
 struct FusedCfg {
+    static_assert(D == 2 || D == 4, "pipeline depth (tiles per worker between counted and emitted + 1)");
     static_assert(WG <= 16, "the chain warp scans the worker functions in one half warp");
     static_assert((WG * R * 512) % 16 == 0, "tiles start on 16-byte boundaries");
     static_assert(R % 2 == 0, "the emit scan packs two rounds per word");
@@ -79,8 +85,8 @@ struct FusedCfg {
     static constexpr int OFF_STAGE = PairsFE::TABLE_BYTES;  // + up to 128 bytes of alignment slack
     static constexpr int OFF_BUF = OFF_STAGE + WG * STAGE_BYTES + 128;
     static constexpr int OFF_GS = OFF_BUF + BUF;
-    static constexpr int SMEM = OFF_GS + 2048;
-    static_assert(sizeof(FusedShared) <= 2048, "control block");
+    static constexpr int SMEM = OFF_GS + 4096;
+    static_assert(sizeof(FusedShared) <= 4096, "control block");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -124,7 +130,11 @@ __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *
     return v;
 }
 __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long long v) {
+#ifdef BLT_FZ_ATOM
+    asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %0;" : "+l"(v) : "l"(p) : "memory");
+#else
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
 }
 __device__ __forceinline__ void stg_stream_u32(void *p, uint32_t v) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -376,11 +386,14 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     return ok != 0u;
 }
 
-template <int WG, int R>
+template <int V>
+struct FzIC { static constexpr int value = V; };
+
+template <int WG, int R, int D>
 __global__ void __launch_bounds__((WG + 1) * 32, 1)
 fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsigned long long *__restrict__ desc,
                    uint32_t n_tiles, unsigned long long chunk) {
-    using C = FusedCfg<WG, R>;
+    using C = FusedCfg<WG, R, D>;
     extern __shared__ __align__(16) unsigned char smem[];
     {  // the table, by everybody
         const uint4 *src = reinterpret_cast<const uint4 *>(table);
@@ -396,23 +409,24 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     unsigned char *buf = smem + C::OFF_BUF;
     const uint32_t bar_counted = smem_u32(&gs->counted[0]), bar_resolved = smem_u32(&gs->resolved[0]);
 
-    // ---- prologue: barriers, the geometry of the first two tiles -----------------------------------------------
+    // ---- prologue: barriers, the geometry of the first D tiles -------------------------------------------------
     // Tiles are dealt round-robin: iteration i of this CTA is tile blockIdx.x + i * gridDim.x (every worker can
-    // start the copy of its next slice without asking anybody).
+    // start the copy of its next slice without asking anybody).  Iteration i uses slot i % D of the per-tile state
+    // and slot i % 2D of the geometry.
     const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
     if (warp == WG) {
         if (lane == 0) {
             for (int w = 0; w < WG; ++w) mbar_init(smem_u32(&gs->wbar[w]), 1);
-            mbar_init(bar_counted, 1);
-            mbar_init(bar_counted + 8, 1);
-            gs->arrived[0] = gs->arrived[1] = 0u;
-            mbar_init(bar_resolved, 1);
-            mbar_init(bar_resolved + 8, 1);
+            for (int d = 0; d < D; ++d) {
+                mbar_init(bar_counted + 8 * d, 1);
+                mbar_init(bar_resolved + 8 * d, 1);
+                gs->arrived[d] = 0u;
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             const unsigned long long last_ck = (a.n - 1) / chunk;
-            for (uint32_t j = 0; j < 2; ++j) {
-                const unsigned long long base = ((unsigned long long)tile0 + (unsigned long long)j * tile_step) * C::TILE;
-                fz_tile_geometry<C>(a, chunk, (unsigned long long)tile0 + (unsigned long long)j * tile_step, n_tiles, base / chunk, base % chunk, last_ck, gs, j);
+            for (uint32_t j = 0; j < uint32_t(D); ++j) {
+                const unsigned long long t = (unsigned long long)tile0 + (unsigned long long)j * tile_step;
+                fz_tile_geometry<C>(a, chunk, t, n_tiles, (t * C::TILE) / chunk, (t * C::TILE) % chunk, last_ck, gs, j);
             }
         }
     }
@@ -420,51 +434,60 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
 
     if (warp == WG) {
         // =========================== chain warp ===========================
-        // Two duties that must not block each other: publishing the function of a tile as soon as its workers have
-        // counted it (other CTAs' look-backs wait for it), and resolving the tiles published before.  At most two
-        // tiles are pending: the workers cannot count tile i+1 before they have emitted tile i-1.
-        // geometry of the tile two iterations ahead, advanced without divisions
+        // Resolves the tiles whose functions are published, oldest first.  Up to D tiles are pending: the workers cannot
+        // count tile i before they have emitted tile i-D.
         const unsigned long long last_ck = (a.n - 1) / chunk;
         const unsigned long long step_bytes = (unsigned long long)tile_step * C::TILE;
         const unsigned long long step_ck = step_bytes / chunk, step_rem = step_bytes % chunk;
-        unsigned long long g_ck = (((unsigned long long)tile0 + 2ull * tile_step) * C::TILE) / chunk;
-        unsigned long long g_rem = (((unsigned long long)tile0 + 2ull * tile_step) * C::TILE) % chunk;
-        FzPending pend[2];
-        pend[0].cur = pend[1].cur = 0;
-        uint32_t n_pend = 0;            // pend[0] is the older one
+        // geometry of the tile D iterations ahead, advanced without divisions
+        unsigned long long g_ck = (((unsigned long long)tile0 + (unsigned long long)D * tile_step) * C::TILE) / chunk;
+        unsigned long long g_rem = (((unsigned long long)tile0 + (unsigned long long)D * tile_step) * C::TILE) % chunk;
+        FzPending pend[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) pend[d].cur = 0;
+        uint32_t n_pend = 0;            // pend[0] is the oldest one
         unsigned long long nxt = tile0;  // the next tile of this CTA to be counted
         uint32_t it = 0;                 // its iteration
         uint32_t idle = 0;
+        FZ_PROF(long long pc_spread = 0; long long pc_pick = 0; long long pc_res = 0; long long pc_polls = 0; long long pc_tiles = 0; long long t_pick[D];)
         while (nxt < n_tiles || n_pend != 0) {
             bool progress = false;
-            if (nxt < n_tiles && n_pend < 2 && mbar_test(bar_counted + 8 * (it & 1u), (it >> 1) & 1u)) {
+            if (nxt < n_tiles && n_pend < uint32_t(D) && mbar_test(bar_counted + 8 * (it % D), (it / D) & 1u)) {
                 // tile `nxt` is counted and its function published (by the last worker to finish): take it over
-                const uint32_t par = it & 1u;
+                const uint32_t slot = it % D;
                 FzPending p;
-                const uint32_t tfl = gs->tf_flags[par];
+                const uint32_t tfl = gs->tf_flags[slot];
                 p.tf.id = tfl & 1u; p.tf.cst = (tfl >> 1) & 1u; p.tf.delta = (tfl >> 2) & 1u; p.starts = (tfl >> 3) & 1u;
-                p.tf.cnt0 = gs->tf_cnt[par];
-                const uint32_t efl = gs->ex_flags[par][lane & 15];
+                p.tf.cnt0 = gs->tf_cnt[slot];
+                const uint32_t efl = gs->ex_flags[slot][lane & 15];
                 p.ex.id = efl & 1u; p.ex.cst = (efl >> 1) & 1u; p.ex.delta = (efl >> 2) & 1u;
-                p.ex.cnt0 = gs->ex_cnt[par][lane & 15];
-                p.cur = uint32_t(nxt); p.par = par;
-                // the geometry of the tile two iterations on goes into this tile's slot: every reader of the slot is done
-                // with it (the workers read it before they count); the `resolved` arrive below releases it
-                if (lane == 0) fz_tile_geometry<C>(a, chunk, nxt + 2ull * tile_step, n_tiles, g_ck, g_rem, last_ck, gs, par);
+                p.ex.cnt0 = gs->ex_cnt[slot][lane & 15];
+                p.cur = uint32_t(nxt); p.par = slot;
+                FZ_PROF({ const long long now = clock64(); pc_spread += gs->t_pub[slot] - gs->t_first[slot]; pc_pick += now - gs->t_pub[slot];
+                          for (int d = 0; d < D; ++d) if (uint32_t(d) == n_pend) t_pick[d] = gs->t_pub[slot]; ++pc_tiles; })
+                // the geometry of the tile D iterations on goes into the slot of the tile D iterations back, which every
+                // worker has emitted by now (it counted this one after that); the `resolved` arrive below releases it
+                if (lane == 0)
+                    fz_tile_geometry<C>(a, chunk, nxt + (unsigned long long)D * tile_step, n_tiles, g_ck, g_rem, last_ck, gs, (it + D) % (2 * D));
                 g_ck += step_ck;
                 g_rem += step_rem;
                 if (g_rem >= chunk) { g_rem -= chunk; ++g_ck; }
-                if (n_pend == 0) pend[0] = p; else pend[1] = p;
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    if (uint32_t(d) == n_pend) pend[d] = p;
                 ++n_pend;
                 nxt += tile_step;
                 ++it;
                 progress = true;
             }
+            FZ_PROF(if (n_pend != 0) ++pc_polls;)
             if (n_pend != 0 && fz_chain_poll<WG, C::LB>(a, gs, desc, pend[0], n_tiles, lane)) {
-                const uint32_t par = pend[0].par;
+                const uint32_t slot = pend[0].par;
+                FZ_PROF({ pc_res += clock64() - t_pick[0]; for (int d = 0; d + 1 < D; ++d) t_pick[d] = t_pick[d + 1]; })
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_resolved + 8 * par);  // releases res[par] and the slot written above
-                pend[0] = pend[1];
+                if (lane == 0) mbar_arrive(bar_resolved + 8 * slot);  // releases res[slot] and the geometry written above
+#pragma unroll
+                for (int d = 0; d + 1 < D; ++d) pend[d] = pend[d + 1];
                 --n_pend;
                 progress = true;
             }
@@ -478,6 +501,10 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 idle = 0;
             }
         }
+        FZ_PROF(if (lane == 0 && blockIdx.x < 256) {
+            unsigned long long *pp = g_fz_prof + (size_t(blockIdx.x) * 16 + 15) * 8;
+            pp[0] = pc_spread; pp[1] = pc_pick; pp[2] = pc_res; pp[3] = pc_polls; pp[4] = pc_tiles;
+        })
         return;
     }
 
@@ -490,30 +517,23 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     const uint32_t slice_off = uint32_t(wg * C::WARP_BYTES);
     uint32_t parity = 0;
     if (tile0 < n_tiles) fz_warp_copy<C>(a, tile0, wg, slice, wbar, lane);
-    // the tile counted in the previous iteration: tokens and emit masks stay in registers until its prefix is known
-    uint32_t hvP[R][4], ovP[R][4], emP[R];
-    bool prev_valid = false, prev_full = true;
-    uint32_t prev_len = 0, prev_wall0 = FZ_NO_WALL, prev_wall1 = FZ_NO_WALL;
-    unsigned long long prev_wall_ck0 = 0, prev_wall_ck1 = 0;
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        emP[k] = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { hvP[k][q] = 0; ovP[k][q] = 0; }
-    }
-
-    unsigned long long cur = tile0;  // (64-bit: the tile after the last one may not fit 32 bits)
+    // D sets of retained tiles: tokens and emit masks stay in registers until the tile's prefix is known.  Iteration
+    // `it` counts into set it % D and emits the tile of iteration it - (D-1) from set (it + 1) % D.
+    uint32_t hv[D][R][4], ov[D][R][4], em[D][R];
     FZ_PROF(long long pf_copy = 0; long long pf_count = 0; long long pf_chain = 0; long long pf_emit = 0; long long pf_tiles = 0; long long pf_t = clock64();)
-    for (uint32_t it = 0;; ++it, cur += tile_step) {
-        const uint32_t par = it & 1u;
+
+    auto iteration = [&](auto ns_c, auto os_c, uint32_t it) -> bool {
+        constexpr int NS = decltype(ns_c)::value, OS = decltype(os_c)::value;
+        const unsigned long long cur = (unsigned long long)tile0 + (unsigned long long)it * tile_step;
         const bool have_new = cur < n_tiles;
-        if (!have_new && !prev_valid) break;
-        uint32_t hvN[R][4], ovN[R][4], emN[R];
-        const uint32_t tile_len = gs->len[par];
-        const uint32_t wall0 = gs->wall[par][0], wall1 = gs->wall[par][1];  // chunk-last elements in this tile, if any
-        const unsigned long long wall_ck0 = gs->wall_ck[par][0], wall_ck1 = gs->wall_ck[par][1];
-        const bool full = tile_len == uint32_t(C::TILE);
+        const bool have_old = it >= uint32_t(D - 1) &&
+                              (unsigned long long)tile0 + (unsigned long long)(it - uint32_t(D - 1)) * tile_step < n_tiles;
+        if (!have_new && !have_old) return false;
         if (have_new) {
+            const uint32_t slot = it % D, gslot = it % (2 * D);
+            const uint32_t tile_len = gs->len[gslot];
+            const uint32_t wall0 = gs->wall[gslot][0], wall1 = gs->wall[gslot][1];  // chunk-last elements in this tile, if any
+            const bool full = tile_len == uint32_t(C::TILE);
             FZ_PROF(pf_t = clock64();)
             if (!mbar_wait<20>(wbar, parity)) *a.scratch.overflow = 3u;
             parity ^= 1u;
@@ -528,8 +548,8 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 const uint4 w = *reinterpret_cast<const uint4 *>(slice + k * 512 + lane * 16);
                 uint32_t next = __shfl_down_sync(FULL, w.x & 0xffu, 1);
                 if (lane == 31) next = slice[k * 512 + 512];
-                fz_lookup<0>(tbl_s, w, next, hvN[k]);
-                fz_lookup<1>(tbl_s, w, next, ovN[k]);
+                fz_lookup<0>(tbl_s, w, next, hv[NS][k]);
+                fz_lookup<1>(tbl_s, w, next, ov[NS][k]);
                 uint32_t valid = 0xFFFFu;
                 if (!full) valid = (off + 16 <= tile_len) ? 0xFFFFu : (off < tile_len ? ((1u << (tile_len - off)) - 1u) : 0u);
                 if (wall0 - round_off < 512u || wall1 - round_off < 512u) {  // warp-uniform: a wall is in this round
@@ -539,12 +559,12 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     for (int j = 0; j < 16; ++j) {
                         if (dj0 == uint32_t(j) || dj1 == uint32_t(j)) {
                             const uint32_t be = PairsFE::raw_be(w, j);
-                            uint32_t &dst = (j & 1) ? ovN[k][j >> 2] : hvN[k][j >> 2];
+                            uint32_t &dst = (j & 1) ? ov[NS][k][j >> 2] : hv[NS][k][j >> 2];
                             dst = ((j >> 1) & 1) ? ((dst & 0x0000ffffu) | (be << 16)) : ((dst & 0xffff0000u) | be);
                         }
                     }
                 }
-                const uint32_t m = fz_membership(hvN[k], ovN[k]) & valid;
+                const uint32_t m = fz_membership(hv[NS][k], ov[NS][k]) & valid;
                 const uint32_t lead = __clz(~(m << 16));  // ones at the top of the segment
                 const uint32_t nid = ~__ballot_sync(FULL, m == 0xFFFFu);
                 const uint32_t cob = __ballot_sync(FULL, (lead & 1u) != 0);
@@ -552,9 +572,9 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 const uint32_t l_nid = nid & lt_mask;
                 const uint32_t cin0 = l_nid ? ((cob >> (31 - __clz(l_nid))) & 1u) : c_round0;
                 const uint32_t st = start_bits(m, cin0);
-                const uint32_t em = valid & ~((st << 1) | cin0);
-                const uint32_t cnt = __popc(em);
-                emN[k] = em;
+                const uint32_t e = valid & ~((st << 1) | cin0);
+                const uint32_t cnt = __popc(e);
+                em[NS][k] = e;
                 cnt0 += __reduce_add_sync(FULL, cnt);
                 if (nid) {
                     if (t_id) {  // the slice's first non-identity segment is the only one whose count sees the slice's carry_in
@@ -572,39 +592,46 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             else __syncwarp();
             uint32_t last = 0;
             if (lane == 0) {
-                gs->fn_flags[par][wg] = (t_id ? 1u : 0u) | (t_const << 1) | (delta << 2);
-                gs->fn_cnt[par][wg] = cnt0;
+                gs->fn_flags[slot][wg] = (t_id ? 1u : 0u) | (t_const << 1) | (delta << 2);
+                gs->fn_cnt[slot][wg] = cnt0;
                 __threadfence_block();
-                last = (atomicAdd(&gs->arrived[par], 1u) == uint32_t(WG - 1)) ? 1u : 0u;
+                const uint32_t order = atomicAdd(&gs->arrived[slot], 1u);
+                last = (order == uint32_t(WG - 1)) ? 1u : 0u;
+                FZ_PROF(if (order == 0u) gs->t_first[slot] = clock64();)
             }
             last = __shfl_sync(FULL, last, 0);
             if (last) {
                 // the last worker to finish composes the WG functions and publishes the tile's function right away (no
                 // detour through the chain warp: other CTAs' look-backs are waiting for it), then hands the tile over
                 __threadfence_block();
-                if (lane == 0) gs->arrived[par] = 0u;
-                const FzPending p = fz_chain_publish<WG>(gs, desc, uint32_t(cur), gs->flags[par], par, lane);
+                if (lane == 0) gs->arrived[slot] = 0u;
+                const FzPending p = fz_chain_publish<WG>(gs, desc, uint32_t(cur), gs->flags[gslot], slot, lane);
                 if (lane < WG) {
-                    gs->ex_flags[par][lane] = p.ex.id | (p.ex.cst << 1) | (p.ex.delta << 2);
-                    gs->ex_cnt[par][lane] = p.ex.cnt0;
+                    gs->ex_flags[slot][lane] = p.ex.id | (p.ex.cst << 1) | (p.ex.delta << 2);
+                    gs->ex_cnt[slot][lane] = p.ex.cnt0;
                 }
                 if (lane == 0) {
-                    gs->tf_flags[par] = p.tf.id | (p.tf.cst << 1) | (p.tf.delta << 2) | (p.starts << 3);
-                    gs->tf_cnt[par] = p.tf.cnt0;
+                    gs->tf_flags[slot] = p.tf.id | (p.tf.cst << 1) | (p.tf.delta << 2) | (p.starts << 3);
+                    gs->tf_cnt[slot] = p.tf.cnt0;
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_counted + 8 * par);
+                FZ_PROF(if (lane == 0) gs->t_pub[slot] = clock64();)
+                if (lane == 0) mbar_arrive(bar_counted + 8 * slot);
             }
             FZ_PROF({ const long long t1 = clock64(); pf_count += t1 - pf_t; pf_t = t1; })
         }
 
-        // ---- emit (one tile behind): compaction of the retained tokens of the whole slice, streamed out in words ----
-        if (prev_valid) {
-            const uint32_t pp = par ^ 1u;
+        // ---- emit (D-1 tiles behind): compaction of the retained tokens of the whole slice, streamed out in words ----
+        if (have_old) {
+            const uint32_t jt = it - uint32_t(D - 1);
+            const uint32_t slot = jt % D, gslot = jt % (2 * D);
+            const uint32_t old_len = gs->len[gslot];
+            const uint32_t old_wall0 = gs->wall[gslot][0], old_wall1 = gs->wall[gslot][1];
+            const bool old_full = old_len == uint32_t(C::TILE);
             FZ_PROF(pf_t = clock64();)
-            if (!mbar_wait<100>(bar_resolved + 8 * pp, ((it - 1) >> 1) & 1u)) *a.scratch.overflow = 3u;
+            if (!mbar_wait<100>(bar_resolved + 8 * slot, (jt / D) & 1u)) *a.scratch.overflow = 3u;
             FZ_PROF({ const long long t1 = clock64(); pf_chain += t1 - pf_t; pf_t = t1; })
-            const unsigned long long rv = gs->res[pp][wg];
+            const unsigned long long rv = gs->res[slot][wg];
             const uint32_t slice_carry = uint32_t(rv >> 63);
             const unsigned long long rel0 = rv & ~R_CARRY;  // tokens of the launch in front of the slice
             const unsigned long long abs0 = rel0 + a.out_base_tokens;
@@ -620,12 +647,12 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     if (dep) {  // warp-uniform
                         const uint32_t off = slice_off + uint32_t(k * 512 + lane * 16);
                         uint32_t valid = 0xFFFFu;
-                        if (!prev_full) valid = (off + 16 <= prev_len) ? 0xFFFFu : (off < prev_len ? ((1u << (prev_len - off)) - 1u) : 0u);
-                        const uint32_t m = fz_membership(hvP[k], ovP[k]) & valid;
+                        if (!old_full) valid = (off + 16 <= old_len) ? 0xFFFFu : (off < old_len ? ((1u << (old_len - off)) - 1u) : 0u);
+                        const uint32_t m = fz_membership(hv[OS][k], ov[OS][k]) & valid;
                         const uint32_t nid = ~__ballot_sync(FULL, m == 0xFFFFu);
                         if ((nid & lt_mask) == 0u) {
                             const uint32_t st1 = start_bits(m, 1u);
-                            emP[k] = valid & ~((st1 << 1) | 1u);
+                            em[OS][k] = valid & ~((st1 << 1) | 1u);
                         }
                         if (nid) dep = false;
                     }
@@ -634,7 +661,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             // token counts of all rounds at once: two rounds per scanned word
             uint32_t pk[R / 2];
 #pragma unroll
-            for (int h = 0; h < R / 2; ++h) pk[h] = __popc(emP[2 * h]) | (__popc(emP[2 * h + 1]) << 16);
+            for (int h = 0; h < R / 2; ++h) pk[h] = __popc(em[OS][2 * h]) | (__popc(em[OS][2 * h + 1]) << 16);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
@@ -648,18 +675,19 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
 #pragma unroll
             for (int h = 0; h < R / 2; ++h) {
                 const uint32_t tot = __shfl_sync(FULL, pk[h], 31);
-                pos[2 * h] = have + (pk[h] & 0xffffu) - __popc(emP[2 * h]);
+                pos[2 * h] = have + (pk[h] & 0xffffu) - __popc(em[OS][2 * h]);
                 have += tot & 0xffffu;
-                pos[2 * h + 1] = have + (pk[h] >> 16) - __popc(emP[2 * h + 1]);
+                pos[2 * h + 1] = have + (pk[h] >> 16) - __popc(em[OS][2 * h + 1]);
                 have += tot >> 16;
             }
-            if (a.chunk_ends != nullptr) {  // chunks that end in this slice: their output ends behind the wall's token
+            if (a.chunk_ends != nullptr && (old_wall0 & old_wall1) != FZ_NO_WALL) {  // chunks that end in this tile
+                const unsigned long long ck0 = gs->wall_ck[gslot][0], ck1 = gs->wall_ck[gslot][1];
 #pragma unroll
-                for (int k = 0; k < R; ++k) {
+                for (int k = 0; k < R; ++k) {  // their output ends behind the wall's token
                     const uint32_t off = slice_off + uint32_t(k * 512 + lane * 16);
-                    const uint32_t dj0 = prev_wall0 - off, dj1 = prev_wall1 - off;  // 0 .. 15 in the wall's lane only
-                    if (dj0 < 16u) a.chunk_ends[prev_wall_ck0] = a.chunk_ends_base + 2ull * (rel0 + pos[k] + __popc(emP[k] & ((2u << dj0) - 1u)));
-                    if (dj1 < 16u) a.chunk_ends[prev_wall_ck1] = a.chunk_ends_base + 2ull * (rel0 + pos[k] + __popc(emP[k] & ((2u << dj1) - 1u)));
+                    const uint32_t dj0 = old_wall0 - off, dj1 = old_wall1 - off;  // 0 .. 15 in the wall's lane only
+                    if (dj0 < 16u) a.chunk_ends[ck0] = a.chunk_ends_base + 2ull * (rel0 + pos[k] + __popc(em[OS][k] & ((2u << dj0) - 1u)));
+                    if (dj1 < 16u) a.chunk_ends[ck1] = a.chunk_ends_base + 2ull * (rel0 + pos[k] + __popc(em[OS][k] & ((2u << dj1) - 1u)));
                 }
             }
             const bool fits = (abs0 + have <= a.out_cap_tokens);
@@ -667,12 +695,12 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             // dense slice: every lane emits exactly the 8 tokens of one parity in every round
             uint32_t x_or = 0, x_and = 0xFFFFu;
 #pragma unroll
-            for (int k = 0; k < R; ++k) { x_or |= emP[k] ^ 0x5555u; x_and &= emP[k] ^ 0x5555u; }
+            for (int k = 0; k < R; ++k) { x_or |= em[OS][k] ^ 0x5555u; x_and &= em[OS][k] ^ 0x5555u; }
             const bool dense0 = __all_sync(FULL, x_or == 0u), dense1 = __all_sync(FULL, x_and == 0xFFFFu);
             if (fits && (dense0 || dense1) && (abs0 & 7ull) == 0) {
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
-                    const uint32_t *tv = dense0 ? hvP[k] : ovP[k];
+                    const uint32_t *tv = dense0 ? hv[OS][k] : ov[OS][k];
                     stg_stream_v4(a.out + abs0 + size_t(k) * 256 + size_t(lane) * 8, make_uint4(tv[0], tv[1], tv[2], tv[3]));
                 }
             } else if (fits) {
@@ -684,7 +712,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 for (int j = 0; j < 16; ++j) {
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
-                        const uint32_t v = (j & 1) ? ovP[k][j >> 2] : hvP[k][j >> 2];
+                        const uint32_t v = (j & 1) ? ov[OS][k][j >> 2] : hv[OS][k][j >> 2];
                         const uint32_t tok = ((j >> 1) & 1) ? (v >> 16) : v;
                         asm volatile(
                             "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
@@ -695,7 +723,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                             "@p st.shared.u16 [t], %1;\n\t"
                             "@p mad.lo.u32 %0, %0, 1, 2;\n\t}"
                             : "+r"(sp[k])
-                            : "h"(uint16_t(tok)), "r"(emP[k] & (1u << j))
+                            : "h"(uint16_t(tok)), "r"(em[OS][k] & (1u << j))
                             : "memory");
                     }
                 }
@@ -717,28 +745,24 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     const uint32_t word = lds_u32(stage_s + i * 128u + (lane4 ^ (((w7 + i) & 7u) << 2)));
                     if (i * 32u + uint32_t(lane) < nw) stg_stream_u32(gout + i * 128u + lane4, word);
                 }
-                if ((total & 1u) && total - 1u >= head && total != 0u && lane == 0) {
-                    uint32_t last;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(last) : "r"(stage_swz(stage_s + 2u * (total - 1u))) : "memory");
-                    if (!(total == 1u && head == 1u)) *reinterpret_cast<uint16_t *>(gout + 2u * (total - 1u)) = uint16_t(last);
+                if ((total & 1u) && total - 1u >= head && !(total == 1u && head == 1u) && lane == 0) {
+                    uint32_t lastv;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lastv) : "r"(stage_swz(stage_s + 2u * (total - 1u))) : "memory");
+                    *reinterpret_cast<uint16_t *>(gout + 2u * (total - 1u)) = uint16_t(lastv);
                 }
                 __syncwarp();
             }
+            FZ_PROF({ const long long t1 = clock64(); pf_emit += t1 - pf_t; pf_t = t1; })
         }
-        FZ_PROF(if (prev_valid) { const long long t1 = clock64(); pf_emit += t1 - pf_t; pf_t = t1; })
-        // the tile just counted becomes the one to emit
-        prev_valid = have_new;
-        prev_full = full;
-        prev_len = tile_len;
-        prev_wall0 = wall0;
-        prev_wall1 = wall1;
-        prev_wall_ck0 = wall_ck0;
-        prev_wall_ck1 = wall_ck1;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            emP[k] = emN[k];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { hvP[k][q] = hvN[k][q]; ovP[k][q] = ovN[k][q]; }
+        return true;
+    };
+
+    for (uint32_t it = 0;; it += uint32_t(D)) {
+        if (!iteration(FzIC<0>{}, FzIC<1 % D>{}, it)) break;
+        if (!iteration(FzIC<1>{}, FzIC<2 % D>{}, it + 1)) break;
+        if constexpr (D == 4) {
+            if (!iteration(FzIC<2>{}, FzIC<3>{}, it + 2)) break;
+            if (!iteration(FzIC<3>{}, FzIC<0>{}, it + 3)) break;
         }
     }
     FZ_PROF(if (lane == 0 && blockIdx.x < 256) {
@@ -749,14 +773,14 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     })
 }
 
-template <int WG, int R>
+template <int WG, int R, int D>
 struct FusedLaunch {
-    using C = FusedCfg<WG, R>;
+    using C = FusedCfg<WG, R, D>;
     static cudaError_t configure(int dev) {
         static std::atomic<bool> configured[kMaxDevices];
         if (dev >= kMaxDevices) return cudaErrorInvalidDevice;
         if (!configured[dev].load(std::memory_order_acquire)) {
-            cudaError_t err = cudaFuncSetAttribute(fused_sweep_kernel<WG, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+            cudaError_t err = cudaFuncSetAttribute(fused_sweep_kernel<WG, R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
             if (err != cudaSuccess) return err;
             configured[dev].store(true, std::memory_order_release);
         }
@@ -783,7 +807,7 @@ struct FusedLaunch {
         size_t grid = tiles;
         if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
         const size_t chunk = (a.chunk == 0 || a.chunk > a.n) ? a.n : a.chunk;
-        fused_sweep_kernel<WG, R><<<dim3(unsigned(grid)), dim3(C::THREADS), C::SMEM, stream>>>(
+        fused_sweep_kernel<WG, R, D><<<dim3(unsigned(grid)), dim3(C::THREADS), C::SMEM, stream>>>(
             a, d_table, reinterpret_cast<unsigned long long *>(a.scratch.meta), uint32_t(tiles), (unsigned long long)chunk);
         return cudaGetLastError();
     }

@@ -163,7 +163,7 @@ def test_fused_sweep_vs_oracle(nat, torch_mod, oracle, variant, monkeypatch):
     tiles, and a chunk size shorter than a tile, which it must hand to the three-kernel sweep."""
     monkeypatch.setenv("BLT_SWEEP_VARIANT", str(variant))
     monkeypatch.setenv("BLT_DENSE", "0")
-    tile = 30720 if variant == 3 else 16384   # 15 or 8 worker warps x 4 rounds x 512 bytes
+    tile = 30720 if variant == 3 else 15360   # 15 worker warps x 4 or 2 rounds x 512 bytes
     c = nat.Context(0)
     rng = random.Random(3000 + variant)
     sizes = [1, 2, 15, 16, 17, 31, 33, 511, 512, 513, 4097, tile - 1, tile, tile + 1, tile + 15, tile + 16, tile + 17,
@@ -641,7 +641,7 @@ def test_no_writes_outside_the_buffers(nat, torch_mod, oracle, variant, dense, m
     stream = torch.cuda.current_stream().cuda_stream
     for n, chunk in ((6, 0), (15, 0), (21, 0), (35, 16), (253, 2), (253, 16), (2119, 16), (4095, 2047), (4097, 4096),
                      (2 * 4096 - 5, 4096), (70001, 1000), (1 * MiB + 9, 65536),
-                     (32768, 0), (32769, 32768), (3 * 32768 + 17, 32768), (5 * 16384 - 1, 16384), (1 * MiB + 9, 0)):
+                     (32768, 0), (32769, 32768), (3 * 32768 + 17, 32768), (5 * 15360 - 1, 15360), (7 * 30720 + 3, 30720), (1 * MiB + 9, 0)):
         data = rng.choice(np.array([97, 98, 99], dtype=np.uint8), size=n)
         eff = chunk if chunk and chunk < n else n
         nc = (n + eff - 1) // eff

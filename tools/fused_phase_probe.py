@@ -29,6 +29,11 @@ for cfg in (2, 3):
         s.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), 2 * n, 0, st, sync=True)
     buf = np.zeros(256 * 16 * 8, dtype=np.uint64)
     assert nat.lib().blt_debug_fused_profile(buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size)) == 0
+    ch = buf.reshape(256, 16, 8).astype(np.float64)[:148, 15]
+    print(json.dumps({"config": cfg, "chain_warp_per_tile": {"first_to_last_worker_cycles": round(float((ch[:, 0] / ch[:, 4]).mean())),
+                      "publish_to_pickup_cycles": round(float((ch[:, 1] / ch[:, 4]).mean())),
+                      "publish_to_resolved_cycles": round(float((ch[:, 2] / ch[:, 4]).mean())),
+                      "polls": round(float((ch[:, 3] / ch[:, 4]).mean()), 2)}}), flush=True)
     p = buf.reshape(256, 16, 8).astype(np.float64)[:148, :15]
     tot = p[:, :, 0:4].sum(axis=2)
     frac = p[:, :, 0:4] / tot[:, :, None]
