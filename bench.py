@@ -9,6 +9,14 @@ A "step" is one pass of the hot path over one 1 GiB batch per GPU (configs[2] of
   roofline  algorithmic bytes (N_in + 2*T_out) / average kernel duration (CUDA events around every
             launch) against the measured HBM peak of MEASURED_PEAKS.json
   cpu_baseline  the C++ oracle (restated reference, `kind: port`) on a bounded sample, all host threads
+  exact     a second, non-degenerate workload (mixed corpus: > 200 distinct bytes, every pair occurs, the 32 768-rule
+            table is a strict subset of the observed pairs): the dense speculation never holds there, so this is the
+            exact single-pass sweep (greedy leftmost run parity + look-back compaction): roofline_exact,
+            dense_hit_rate, t_out_over_n_in
+  e2e_chunk_api  blt_process_chunk (the reference's TokenizationStrategy::process_chunk) on pageable 16 MiB slices
+            from 1 and 8 calling threads, as pipeline.rs:141-150 would call it
+  file_to_file  blt_run_tokenizer (pipeline.rs:56-131) tmpfs file -> tmpfs file on N GPUs: configs[2] and, when the
+            box has the memory, configs[4] (8 GiB, 60 000 rules); input GB/s, wall, fraction of the PCIe roofline
 Multi-GPU: one process per GPU (torchrun), every rank tokenizes its own 1 GiB shard (weak scaling),
 no data-path collective; only the timing is reduced (max over ranks).
 
@@ -39,14 +47,34 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def build_workload(n_bytes: int, rank: int, n_merges: int, out=None):
-    """Rank r's shard: config-3 text with seed SEED + r; the merges table always comes from the first
-    16 MiB of the rank-0 stream so that every rank uses the same table."""
-    from blt_b200 import synth
-    data = synth.text(n_bytes, SEED + rank, out=out)
-    sample = data if rank == 0 else synth.text(min(n_bytes, synth.MERGE_SAMPLE_BYTES), SEED)
+def load_synth():
+    """blt_b200/synth.py as a stand-alone module (ctypes over libblt_synth.so): importing the package would map
+    libblt_cuda.so, which the reference arm must not touch."""
+    import importlib.util
+    if "blt_bench_synth" in sys.modules:
+        return sys.modules["blt_bench_synth"]
+    spec = importlib.util.spec_from_file_location("blt_bench_synth", os.path.join(ROOT, "blt_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["blt_bench_synth"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build_workload(n_bytes: int, rank: int, n_merges: int, out=None, kind: str = "text"):
+    """Rank r's shard: config-3 text (or the mixed corpus) with seed + r; the merges table always comes from the
+    first 16 MiB of the rank-0 stream so that every rank uses the same table."""
+    synth = load_synth()
+    gen, seed = (synth.text, SEED) if kind == "text" else (synth.mixed, synth.SEED_MIXED)
+    data = gen(n_bytes, seed + rank, out=out)
+    sample = data if rank == 0 else gen(min(n_bytes, synth.MERGE_SAMPLE_BYTES), seed)
     left, right = synth.merges_from_sample(sample, n_merges)
     return data, left, right
+
+
+def workload_config(args):
+    """The `config` object, identical in both arms."""
+    return {"workload": f"BPE {args.merges} merges (u16 vocab), {args.bytes >> 20} MiB synthetic English-like text per GPU, "
+                        f"16 MiB chunks (BASELINE.json configs[2])"}
 
 
 class ClockSampler:
@@ -137,10 +165,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->u16", "data": "synthetic",
-        "config": {"workload": f"BPE {args.merges} merges (u16 vocab), {n >> 20} MiB synthetic English-like text per GPU, "
-                               f"16 MiB chunks, device-resident (BASELINE.json configs[2])",
-                   "note": "reference arm: the same workload on the host cores (restated CPU path, in memory), "
-                           "each step = a bounded prefix of it"},
+        "config": workload_config(args),
+        "notes": {"arm": "the same workload on the host cores (restated CPU path, in memory), each step = a bounded prefix of it"},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
                          "sample": f"first {sample >> 20} MiB of the workload per step, in memory, {threads} threads"},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -178,6 +204,109 @@ def pcie_probe(torch, h_in, h_out, d_in, d_out, n):
     return {"h2d": run(True, False), "d2h": run(False, True), "both_directions_each": run(True, True)}
 
 
+def check_against_oracle(np, data, left, right, chunk, d_out, d_ends, out_bytes):
+    """Whole-output comparison with the oracle (multi-threaded C++ restatement): every byte and every chunk end."""
+    from oracle import oracle_ffi as ora
+    pairs = {(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(left, right))}
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    want = ora.run_buffer("bpe", data, chunk, threads, ora.Merges(pairs))
+    dt = time.perf_counter() - t0
+    got = d_out[:out_bytes].cpu().numpy()
+    if want.size != out_bytes or not np.array_equal(got, want):
+        raise SystemExit("PARITY FAILURE: device-resident output differs from the oracle")
+    ends = d_ends.cpu().numpy()
+    if int(ends[-1]) != out_bytes or np.any(np.diff(ends) <= 0):
+        raise SystemExit("PARITY FAILURE: chunk ends")
+    return f"whole output ({out_bytes} bytes) and {ends.size} chunk ends equal to the oracle's ({dt:.1f}s on {threads} threads)"
+
+
+def time_resident(torch, strat, d_in, n, chunk, d_out, d_ends, stream, steps, warmup):
+    """`steps` launches of blt_process_resident with CUDA events around each; returns (mean ms per launch, out_bytes)."""
+    for _ in range(warmup):
+        strat.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), d_out.numel(), d_ends.data_ptr(), stream, sync=False)
+    out_bytes, _ = strat.resident_result(stream)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        a.record()
+        strat.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), d_out.numel(), d_ends.data_ptr(), stream, sync=False)
+        b.record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / len(evs), out_bytes
+
+
+def chunk_api_leg(np, strat, data, chunk, want, threads_list=(1, 8)):
+    """blt_process_chunk from T host threads on pageable slices of one buffer (the reference's mmap) into fresh
+    pageable outputs (its Vec<u8>), results consumed in chunk order: what `impl TokenizationStrategy` costs."""
+    n = data.size
+    n_chunks = (n + chunk - 1) // chunk
+    pageable = np.array(data, copy=True)          # NOT the pinned buffer: the reference hands in slices of an mmap
+    res = {}
+    for T in threads_list:
+        best, outs = None, None
+        for _ in range(2):
+            outs = [None] * n_chunks
+            nxt = [0]
+            lock = threading.Lock()
+
+            def worker():
+                while True:
+                    with lock:
+                        k = nxt[0]
+                        nxt[0] += 1
+                    if k >= n_chunks:
+                        return
+                    buf = np.empty(2 * chunk, dtype=np.uint8)
+                    outs[k] = strat.process_chunk(pageable[k * chunk:(k + 1) * chunk], out=buf)
+
+            t0 = time.perf_counter()
+            ths = [threading.Thread(target=worker) for _ in range(T)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        if want is not None and not np.array_equal(np.concatenate(outs), want):
+            raise SystemExit("PARITY FAILURE: blt_process_chunk output differs")
+        res[f"callers_{T}"] = round(n / best / 1e9, 2)
+    return {"unit": "GB/s", **res, "buffers": "pageable input slices, fresh pageable output per chunk", "chunk_bytes": chunk,
+            "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(want.size) if want is not None else None}
+
+
+def file_leg(np, nat, synth, name, data, left, right, n_gpus, pcie, want=None, reps=3):
+    """blt_run_tokenizer tmpfs -> tmpfs on n_gpus GPUs of this process; wall = the whole call (config, mmap, contexts
+    on first use, pipeline, trim).  frac_of_pcie_roofline = max(N_in / BW_h2d, out / BW_d2h) / pipeline time."""
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    inp, outp, mp = (os.path.join(d, f"blt_bench_{os.getpid()}_{name}.{e}") for e in ("in", "out", "merges.txt"))
+    try:
+        data.tofile(inp)
+        synth.write_merges_file(mp, left, right)
+        walls = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            nat.run_tokenizer(inp, outp, merges_file=mp, chunk_size="16MB", num_gpus=n_gpus)
+            walls.append(time.perf_counter() - t0)
+        out_bytes = os.path.getsize(outp)
+        if want is not None:
+            got = np.memmap(outp, dtype=np.uint8, mode="r")
+            if got.size != want.size or not np.array_equal(got, want):
+                raise SystemExit(f"PARITY FAILURE: file-to-file output of {name} differs")
+            del got
+        best = min(walls)
+        bw_in = pcie["h2d"] * (n_gpus if n_gpus > 1 and "all_ranks_both_directions_each" not in pcie else 1)
+        bw_out = pcie["d2h"] * (n_gpus if n_gpus > 1 and "all_ranks_both_directions_each" not in pcie else 1)
+        if "all_ranks_both_directions_each" in pcie:
+            bw_in = bw_out = pcie["all_ranks_both_directions_each"]
+        t_roof = max(data.size / (bw_in * 1e9), out_bytes / (bw_out * 1e9))
+        return {"workload": name, "gpus": n_gpus, "bytes_in": int(data.size), "bytes_out": int(out_bytes),
+                "wall_s_first_call": round(walls[0], 3), "wall_s_best": round(best, 3), "input_GBps": round(data.size / best / 1e9, 2),
+                "pcie_roofline_s": round(t_roof, 4), "frac_of_pcie_roofline": round(t_roof / best, 3), "filesystem": d}
+    finally:
+        for f in (inp, outp, mp):
+            if os.path.exists(f):
+                os.unlink(f)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -202,7 +331,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     data, left, right = build_workload(n, rank, args.merges, out=h_in.numpy())
     log(f"[rank {rank}] generated {n >> 20} MiB in {time.perf_counter() - t0:.1f}s")
-    from blt_b200 import synth
+    synth = load_synth()
     with tempfile.NamedTemporaryFile("w", suffix=".merges.txt", delete=False) as f:
         merges_path = f.name
     synth.write_merges_file(merges_path, left, right)
@@ -225,21 +354,10 @@ def run_ours(args):
     out_bytes, sweeps = strat.resident_result(stream)
     t_out = out_bytes // 2
 
-    # ---- parity spot check against the oracle (outside every timed region) ----
+    # ---- parity against the oracle: the WHOLE output and every chunk end (outside every timed region) ----
     parity = None
     if not args.no_check:
-        from oracle import oracle_ffi as ora
-        pairs = {(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(left, right))}
-        om = ora.Merges(pairs)
-        ends = d_ends.cpu().numpy()
-        assert int(ends[-1]) == out_bytes
-        for k in sorted({0, n_chunks - 1, n_chunks // 2, (7 * n_chunks) // 11}):
-            lo = 0 if k == 0 else int(ends[k - 1])
-            got = d_out[lo:int(ends[k])].cpu().numpy()
-            want = np.frombuffer(ora.process_chunk("bpe", data[k * chunk:(k + 1) * chunk], om), dtype=np.uint8)
-            if not np.array_equal(got, want):
-                raise SystemExit(f"PARITY FAILURE in chunk {k}")
-        parity = "oracle-checked chunks 0, mid, 7/11, last"
+        parity = check_against_oracle(np, data, left, right, chunk, d_out, d_ends, out_bytes)
 
     # ---- timed region: device resident ----
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -318,10 +436,11 @@ def run_ours(args):
                "ms_per_step": round(e_ms / e_steps, 3)}
 
     clocks = sampler.stop()   # sampled from just before the device-resident region to the end of the e2e region
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return   # rank 0 alone runs the informational legs below (chunk API, exact workload, file to file on all N GPUs)
 
     # ---- roofline of the sweep kernel ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -354,20 +473,89 @@ def run_ours(args):
         cpu_baseline = {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
                         "sample": f"first {sample >> 20} MiB of the workload, in memory, {threads} threads, {dt:.1f}s"}
 
+    # ---- the drop-in call itself: blt_process_chunk on pageable slices (rank 0, its own GPU) ----
+    e2e_chunk_api = None
+    if not args.no_e2e:
+        want = h_out[:out_bytes].numpy() if e2e is not None else None
+        e2e_chunk_api = chunk_api_leg(np, strat, data, chunk, want)
+
+    # ---- non-degenerate workload: the exact sweep ----
+    exact = None
+    if not args.no_exact:
+        t0 = time.perf_counter()
+        mdata, mleft, mright = build_workload(n, 0, args.merges, out=h_in.numpy(), kind="mixed")   # reuses the pinned input buffer
+        log(f"[rank 0] generated {n >> 20} MiB of mixed corpus in {time.perf_counter() - t0:.1f}s")
+        mstrat = ctx.bpe_from_pairs({(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(mleft, mright))})
+        d_in.copy_(h_in)
+        x_steps = max(3, min(args.steps, 20))
+        x_ms, x_out = time_resident(torch, mstrat, d_in, n, chunk, d_out, d_ends, stream, x_steps, 3)
+        x_tok = x_out // 2
+        ends = np.concatenate([[0], d_ends.cpu().numpy()])
+        lens_in = np.minimum(chunk, n - chunk * np.arange(n_chunks))
+        dense_chunks = int(np.sum(np.diff(ends) == 2 * ((lens_in + 1) // 2)))
+        x_parity = None
+        if not args.no_check:
+            x_parity = check_against_oracle(np, mdata, mleft, mright, chunk, d_out, d_ends, x_out)
+        x_alg = n + 2 * x_tok
+        x_ach = x_alg / (x_ms * 1e-3) / 1e9
+        xtraffic = None
+        if os.path.exists(tpath):
+            try:
+                xtraffic = json.load(open(tpath)).get("exact_sweep_dram_bytes_per_launch")
+            except Exception:
+                xtraffic = None
+        exact = {"workload": f"BPE {args.merges} merges on {n >> 20} MiB of a mixed corpus (text, code, UTF-8 script, base64, binary; "
+                             "every byte pair occurs, the table is a strict subset), 16 MiB chunks, device-resident",
+                 "value": round(n / (x_ms * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(x_ms, 4), "steps": x_steps,
+                 "t_out_over_n_in": round(x_tok / n, 4), "dense_hit_rate": round(dense_chunks / n_chunks, 4),
+                 "roofline_exact": {"bound": "hbm", "achieved": round(x_ach, 1), "peak": peak, "unit": "GB/s", "frac": round(x_ach / peak, 4),
+                                    "traffic": xtraffic, "algorithmic_bytes_per_launch": int(x_alg),
+                                    "kernel": "bltk::fused_sweep_kernel (count + decoupled look-back + emit in one pass) behind the dense "
+                                              "pass's predictor (which stops attempting after the first failures)"},
+                 "parity": x_parity}
+        mstrat.close()
+
+    # ---- file to file on all N GPUs from this process (the other ranks have left) ----
+    file_to_file = None
+    if not args.no_file and e2e is not None and e2e.get("pcie_probe_GBps"):
+        pcie = e2e["pcie_probe_GBps"]
+        del d_in, d_out, d_ends
+        torch.cuda.empty_cache()
+        file_to_file = []
+        tdata, tleft, tright = build_workload(n, 0, args.merges, out=h_in.numpy())      # the headline workload again
+        file_to_file.append(file_leg(np, nat, synth, "configs2_text_32768_merges", tdata, tleft, tright, world, pcie,
+                                     want=None if args.no_check else h_out[:out_bytes].numpy()))
+        try:
+            import psutil
+            free = psutil.virtual_memory().available
+            shm_free = os.statvfs("/dev/shm").f_bavail * os.statvfs("/dev/shm").f_frsize if os.path.isdir("/dev/shm") else 0
+        except Exception:
+            free = shm_free = 0
+        n5 = 8 * GIB
+        if min(free, shm_free) > 5 * n5 and not args.no_config5:
+            t0 = time.perf_counter()
+            d5 = synth.text(n5, synth.SEED_CONFIG[5])
+            l5, r5 = synth.merges_from_sample(d5, 60000)
+            log(f"[rank 0] generated config 5 (8 GiB) in {time.perf_counter() - t0:.1f}s")
+            file_to_file.append(file_leg(np, nat, synth, "configs4_8GiB_60000_merges", d5, l5, r5, world, pcie, reps=2))
+            del d5
+        else:
+            file_to_file.append({"workload": "configs4_8GiB_60000_merges", "skipped": f"needs {5 * n5 >> 30} GiB of free RAM and tmpfs "
+                                 f"(have {free >> 30} / {shm_free >> 30} GiB); tests/test_gpu_parity.py::test_config5_file_to_file covers it"})
+
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8->u16", "data": "synthetic",
-        "config": {"workload": f"BPE {args.merges} merges (u16 vocab), {n >> 20} MiB synthetic English-like text per GPU, "
-                               f"16 MiB chunks, device-resident (BASELINE.json configs[2])",
-                   "l2": "inputs larger than L2 (1 GiB in + out per step vs 126 MB L2), no flush needed",
-                   "sweeps": sweeps, "variant": os.environ.get("BLT_SWEEP_VARIANT", "default"), "parity": parity},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": (1 if dense_held else 4) * args.steps,
+        "config": workload_config(args),
+        "notes": {"value": "device-resident: input and output stay in HBM (blt_process_resident)",
+                  "l2": "inputs larger than L2 (1 GiB in + out per step vs 126 MB L2), no flush needed",
+                  "sweeps": sweeps, "variant": os.environ.get("BLT_SWEEP_VARIANT", "default"), "parity": parity},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "exact": exact, "e2e_chunk_api": e2e_chunk_api,
+        "file_to_file": file_to_file, "gpu_launches": (1 if dense_held else 3) * args.steps,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -381,6 +569,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-exact", action="store_true")
+    ap.add_argument("--no-file", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # `python bench.py --gpus N` typed by hand: start the N ranks the driver would start with torchrun

@@ -79,6 +79,8 @@ def lib():
     L.blt_content_type_token.restype = C.c_uint16
     L.blt_shard_chunks.argtypes = [C.c_size_t, C.c_int, szp]
     L.blt_shard_chunks.restype = None
+    L.blt_file_chunk_device.argtypes = [C.c_size_t, C.c_int]
+    L.blt_file_chunk_device.restype = C.c_int
     _lib = L
     return L
 
@@ -130,6 +132,11 @@ def shard_chunks(n_chunks: int, n_gpus: int):
     b = (C.c_size_t * (n_gpus + 1))()
     lib().blt_shard_chunks(n_chunks, n_gpus, b)
     return list(b)
+
+
+def file_chunk_device(chunk_index: int, n_gpus: int) -> int:
+    """The device blt_run_tokenizer gives chunk `chunk_index` on n_gpus devices (round-robin)."""
+    return lib().blt_file_chunk_device(chunk_index, n_gpus)
 
 
 def run_tokenizer(input: Optional[str], output: Optional[str], merges_file: Optional[str] = None,

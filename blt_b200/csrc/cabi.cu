@@ -662,4 +662,6 @@ void blt_shard_chunks(size_t n_chunks, int n_gpus, size_t *bounds) {
     for (int g = 0; g <= n_gpus; ++g) bounds[g] = (size_t(g) * n_chunks + size_t(n_gpus) - 1) / size_t(n_gpus);
 }
 
+int blt_file_chunk_device(size_t chunk_index, int n_gpus) { return n_gpus > 1 ? int(chunk_index % size_t(n_gpus)) : 0; }
+
 }  // extern "C"

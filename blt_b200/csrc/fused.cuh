@@ -39,7 +39,7 @@ constexpr uint32_t FZ_F_START = 2u, FZ_NO_WALL = 0xffffffffu;
 // BLT_FUSED_PROF builds only: per worker (CTA x 16 + worker) x 8 counters, in clock cycles:
 // 0 waiting for the slice copy, 1 counting, 2 waiting for the chain warp, 3 emitting, 4 tiles, 5 SM id
 #ifdef BLT_FUSED_PROF
-__device__ unsigned long long g_fz_prof[256 * 16 * 8];
+__device__ unsigned long long g_fz_prof[256 * 32 * 8];
 #define FZ_PROF(stmt) stmt
 #else
 #define FZ_PROF(stmt)
@@ -48,45 +48,46 @@ __device__ unsigned long long g_fz_prof[256 * 16 * 8];
 constexpr int FZ_DMAX = 4;  // deepest pipeline: tiles a worker holds between "counted" and "emitted"
 
 struct FusedShared {
-    unsigned long long wbar[16];              // per worker: completion of the bulk copy of its slice
+    unsigned long long wbar[32];              // per worker: completion of the bulk copy of its slice
     // per tile in flight, slot = iteration % D:
     unsigned long long counted[FZ_DMAX];      // the tile is counted and its function published: one arrival
     unsigned long long resolved[FZ_DMAX];     // the chain warp has left that tile's prefix in res[slot]: one arrival
     uint32_t arrived[FZ_DMAX];                // workers that have counted it (the last one composes and publishes the function)
     uint32_t tf_flags[FZ_DMAX];               // the tile's function, left for the chain warp by that worker (+ bit3: starts a chunk)
     unsigned long long tf_cnt[FZ_DMAX];
-    uint32_t ex_flags[FZ_DMAX][16];           // per worker: the workers in front of it composed
-    unsigned long long ex_cnt[FZ_DMAX][16];
-    unsigned long long fn_cnt[FZ_DMAX][16];   // per worker: tokens of its slice for carry_in 0
-    uint32_t fn_flags[FZ_DMAX][16];           // per worker: bit0 identity, bit1 constant carry_out, bit2 delta
-    unsigned long long res[FZ_DMAX][16];      // per worker: carry_in << 63 | tokens of the launch in front of its slice
-    // geometry, slot = iteration % (2 D): written D iterations ahead, read when the tile is counted and when it is emitted
-    uint32_t flags[2 * FZ_DMAX];              // FZ_F_START: it starts a chunk (the carry entering it is 0)
-    uint32_t len[2 * FZ_DMAX];                // valid bytes of the tile (the tile size but for the input's last tile)
-    uint32_t wall[2 * FZ_DMAX][2];            // offsets of the (at most two) chunk-last elements inside the tile, else FZ_NO_WALL:
+    uint32_t ex_flags[FZ_DMAX][32];           // per worker: the workers in front of it composed
+    unsigned long long ex_cnt[FZ_DMAX][32];
+    unsigned long long fn_cnt[FZ_DMAX][32];   // per worker: tokens of its slice for carry_in 0
+    uint32_t fn_flags[FZ_DMAX][32];           // per worker: bit0 identity, bit1 constant carry_out, bit2 delta
+    unsigned long long res[FZ_DMAX][32];      // per worker: carry_in << 63 | tokens of the launch in front of its slice
+    // geometry, slot = iteration % (4 D): written D+1 iterations ahead (when the tile is claimed), read when the worker
+    // starts the copy of its slice, when the tile is counted and when it is emitted
+    uint32_t tile_id[4 * FZ_DMAX];            // the tile of that iteration (claimed from the launch's counter); >= n_tiles: none
+    uint32_t flags[4 * FZ_DMAX];              // FZ_F_START: it starts a chunk (the carry entering it is 0)
+    uint32_t len[4 * FZ_DMAX];                // valid bytes of the tile (the tile size but for the input's last tile)
+    uint32_t wall[4 * FZ_DMAX][2];            // offsets of the (at most two) chunk-last elements inside the tile, else FZ_NO_WALL:
                                               //   [0] a chunk boundary, [1] the end of the input if it is another element
-    unsigned long long wall_ck[2 * FZ_DMAX][2];  // the chunks those walls end
+    unsigned long long wall_ck[4 * FZ_DMAX][2];  // the chunks those walls end
     FZ_PROF(long long t_first[FZ_DMAX]; long long t_pub[FZ_DMAX];)  // first / last worker done with the tile (clock64)
 };
 
 template <int WG, int R, int D>
 struct FusedCfg {
     static_assert(D == 2 || D == 4, "pipeline depth (tiles per worker between counted and emitted + 1)");
-    static_assert(WG <= 16, "the chain warp scans the worker functions in one half warp");
+    static_assert(WG <= 31, "the chain warp scans the worker functions in one warp");
     static_assert((WG * R * 512) % 16 == 0, "tiles start on 16-byte boundaries");
     static_assert(R % 2 == 0, "the emit scan packs two rounds per word");
     static constexpr int THREADS = (WG + 1) * 32;  // WG workers + the chain warp
     static constexpr int LB = 6;  // look-back window: 32 * LB tiles (more than the 148 tiles of one round of the deal)
     static constexpr int WARP_BYTES = R * 512;
     static constexpr int TILE = WG * WARP_BYTES;
-    static constexpr int WBUF = WARP_BYTES + 128;  // a worker's slice + the look-ahead vector
+    static constexpr int WBUF = WARP_BYTES + 32;  // a worker's slice + the look-ahead vector
     static constexpr int BUF = WG * WBUF;
-    static constexpr int STAGE_BYTES = (2 * (1 + R * 512) + 127) / 128 * 128;  // per worker: 1 pending + R*512 new tokens
+    static constexpr int STAGE_BYTES = (2 * (8 + R * 512) + 127) / 128 * 128;  // per worker: up to 7 head slots + R*512 tokens + 1 scratch slot
     static constexpr int OFF_STAGE = PairsFE::TABLE_BYTES;  // + up to 128 bytes of alignment slack
     static constexpr int OFF_BUF = OFF_STAGE + WG * STAGE_BYTES + 128;
     static constexpr int OFF_GS = OFF_BUF + BUF;
-    static constexpr int SMEM = OFF_GS + 4096;
-    static_assert(sizeof(FusedShared) <= 4096, "control block");
+    static constexpr int SMEM = OFF_GS + int((sizeof(FusedShared) + 127) / 128 * 128);
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -101,20 +102,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // false: the phase did not complete within seconds (reported as a CUDA error by the host instead of hanging the device).
-// SLEEP: nanoseconds between two looks (a waiting warp must not eat the issue slots of the working ones).
-template <int SLEEP>
+// The warp is suspended by the hardware between two looks (try_wait with a suspend-time hint): a waiting warp issues
+// one instruction per wake-up instead of spinning through the issue slots and the alu pipe of the working ones.
+template <int HINT_NS>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t tries = 0; tries < (1u << 24); ++tries) {
+    for (uint32_t tries = 0; tries < (1u << 22); ++tries) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(uint32_t(HINT_NS))
             : "memory");
         if (ok != 0u) return true;
-        __nanosleep(SLEEP);
     }
     return false;
 }
@@ -151,10 +152,11 @@ __device__ __forceinline__ uint32_t lds_tbl(uint32_t addr) {
     asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-// staging line: shared address of a token -> where it really lives.  Bank bits 2-4 are XORed with the index of the
-// 128-byte window (mod 8), so that stores 4 to 8 words apart (one lane's tokens behind the other's) do not pile up on
-// a few banks.  Every 128-byte window is permuted within itself: lines are whole, 128-byte aligned windows.
-__device__ __forceinline__ uint32_t stage_swz(uint32_t addr) { return addr ^ ((addr >> 5) & 0x1Cu); }
+// staging line: shared address of a token -> where it really lives.  The index of the 16-byte vector inside its
+// 128-byte window (address bits 4-6) is XORed with the index of the window (mod 8), so that the lanes' 2-byte stores
+// (one lane's tokens about 17 bytes behind the other's) do not pile up on a few banks while 16-byte vectors stay whole
+// for the flush.  Every 128-byte window is permuted within itself: lines are whole, 128-byte aligned windows.
+__device__ __forceinline__ uint32_t stage_swz(uint32_t addr) { return addr ^ ((addr >> 3) & 0x70u); }
 
 // The SEG/2 pairs of one 16-byte segment that start at positions of parity PAR: the big-endian u16 to emit at each of
 // those positions (merged id if the pair is a rule, else the element itself), two per register in position order.
@@ -218,27 +220,36 @@ __device__ __forceinline__ void fz_warp_copy(const SweepArgs &a, uint32_t t, int
 }
 
 // Where tile t meets chunk walls - chain lane 0.  Chunks are at least a tile long, so a tile holds at most one chunk
-// boundary; the input's last tile may hold the end of the input as well.  ck / rem: the chunk the tile starts in and
-// its offset in that chunk (tracked incrementally by the caller: no division per tile).
+// boundary; the input's last tile may hold the end of the input as well.
 template <class C>
 __device__ __forceinline__ void fz_tile_geometry(const SweepArgs &a, unsigned long long chunk, unsigned long long t, uint32_t n_tiles,
-                                                 unsigned long long ck, unsigned long long rem, unsigned long long last_ck,
-                                                 FusedShared *gs, uint32_t slot) {
+                                                 unsigned long long last_ck, FusedShared *gs, uint32_t slot) {
     uint32_t flags = 0, wall0 = FZ_NO_WALL, wall1 = FZ_NO_WALL, len = 0;
+    unsigned long long ck = 0;
     if (t < n_tiles) {
         const unsigned long long base = t * C::TILE;
+        ck = base / chunk;
+        const unsigned long long rem = base - ck * chunk;  // the tile's offset in the chunk it starts in
         len = (a.n - base < (unsigned long long)C::TILE) ? uint32_t(a.n - base) : uint32_t(C::TILE);
         if (rem == 0) flags |= FZ_F_START;
         const unsigned long long to_last = chunk - 1 - rem;  // distance to the last element of the chunk the tile starts in
         if (to_last < (unsigned long long)len) wall0 = uint32_t(to_last);
         if (t + 1 == n_tiles && wall0 != len - 1u) wall1 = len - 1u;  // the input's last element ends the last chunk
     }
+    gs->tile_id[slot] = t < n_tiles ? uint32_t(t) : 0xffffffffu;
     gs->flags[slot] = flags;
     gs->len[slot] = len;
     gs->wall[slot][0] = wall0;
     gs->wall[slot][1] = wall1;
     gs->wall_ck[slot][0] = ck;
     gs->wall_ck[slot][1] = last_ck;
+}
+
+// Claims the next tile of the launch (chain lane 0).  Tiles are handed out in the order the CTAs ask for them: a
+// tile's predecessors were claimed - and so are counted - before it, whatever the phase or the speed of their CTAs.
+__device__ __forceinline__ unsigned long long fz_claim(unsigned int *counter, uint32_t n_tiles) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    return t < n_tiles ? t : 0xffffffffull;
 }
 
 // ---- the chain warp ------------------------------------------------------------------------------------------
@@ -292,7 +303,7 @@ __device__ __forceinline__ FzPending fz_chain_publish(FusedShared *gs, unsigned 
 // Position x <-> tile cur-1-x; lane i holds positions i, i+32, ... (word j of a mask = positions 32j .. 32j+31).
 template <int WG, int LB>
 __device__ __forceinline__ bool fz_chain_poll(const SweepArgs &a, FusedShared *gs, unsigned long long *desc, const FzPending &pd,
-                                              uint32_t n_tiles, int lane) {
+                                              uint32_t n_tiles, int lane, uint32_t *prof_holes = nullptr, uint32_t *prof_q = nullptr) {
     const uint32_t cur = pd.cur;
     unsigned long long d[LB];
 #pragma unroll
@@ -318,6 +329,16 @@ __device__ __forceinline__ bool fz_chain_poll(const SweepArgs &a, FusedShared *g
             }
         }
     }
+    FZ_PROF(if (prof_holes != nullptr) {
+        uint32_t nh = 0;  // unpublished tiles in front of the nearest prefix (or in the whole window)
+        for (int j = 0; j < LB; ++j) {
+            const uint32_t zmj = __ballot_sync(FULL, uint32_t(d[j] >> 62) == 0u);
+            if (qw < 0 || j < qw) nh += __popc(zmj);
+            else if (j == qw) nh += __popc(zmj & ((1u << qb) - 1u));
+        }
+        *prof_holes = nh;
+        *prof_q = qw < 0 ? 999u : uint32_t(32 * qw + qb);
+    })
     if (qw < 0 || hole) return false;
     const int q = 32 * qw + qb;
     // The carry leaving position x: P.carry at q, the constant of a non-identity tile, else whatever enters it.
@@ -409,11 +430,12 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     unsigned char *buf = smem + C::OFF_BUF;
     const uint32_t bar_counted = smem_u32(&gs->counted[0]), bar_resolved = smem_u32(&gs->resolved[0]);
 
-    // ---- prologue: barriers, the geometry of the first D tiles -------------------------------------------------
-    // Tiles are dealt round-robin: iteration i of this CTA is tile blockIdx.x + i * gridDim.x (every worker can
-    // start the copy of its next slice without asking anybody).  Iteration i uses slot i % D of the per-tile state
-    // and slot i % 2D of the geometry.
-    const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
+    // ---- prologue: barriers, the first D+1 tiles -----------------------------------------------------------------
+    // Tiles are claimed from one counter of the launch, D+1 iterations ahead of their count (the worker starts the
+    // copy of its next slice one iteration ahead, before it has met the chain warp again).  Iteration i uses slot i % D
+    // of the per-tile state and slot i % 4D of the geometry.
+    constexpr uint32_t GS = 4 * D;
+    unsigned int *claim = reinterpret_cast<unsigned int *>(static_cast<unsigned char *>(a.scratch.ctrl) + 128);
     if (warp == WG) {
         if (lane == 0) {
             for (int w = 0; w < WG; ++w) mbar_init(smem_u32(&gs->wbar[w]), 1);
@@ -424,10 +446,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             const unsigned long long last_ck = (a.n - 1) / chunk;
-            for (uint32_t j = 0; j < uint32_t(D); ++j) {
-                const unsigned long long t = (unsigned long long)tile0 + (unsigned long long)j * tile_step;
-                fz_tile_geometry<C>(a, chunk, t, n_tiles, (t * C::TILE) / chunk, (t * C::TILE) % chunk, last_ck, gs, j);
-            }
+            for (uint32_t j = 0; j <= uint32_t(D); ++j) fz_tile_geometry<C>(a, chunk, fz_claim(claim, n_tiles), n_tiles, last_ck, gs, j);
         }
     }
     __syncthreads();  // table, barriers, first geometry: the only CTA-wide barrier of the kernel
@@ -437,51 +456,55 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         // Resolves the tiles whose functions are published, oldest first.  Up to D tiles are pending: the workers cannot
         // count tile i before they have emitted tile i-D.
         const unsigned long long last_ck = (a.n - 1) / chunk;
-        const unsigned long long step_bytes = (unsigned long long)tile_step * C::TILE;
-        const unsigned long long step_ck = step_bytes / chunk, step_rem = step_bytes % chunk;
-        // geometry of the tile D iterations ahead, advanced without divisions
-        unsigned long long g_ck = (((unsigned long long)tile0 + (unsigned long long)D * tile_step) * C::TILE) / chunk;
-        unsigned long long g_rem = (((unsigned long long)tile0 + (unsigned long long)D * tile_step) * C::TILE) % chunk;
         FzPending pend[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) pend[d].cur = 0;
         uint32_t n_pend = 0;            // pend[0] is the oldest one
-        unsigned long long nxt = tile0;  // the next tile of this CTA to be counted
-        uint32_t it = 0;                 // its iteration
+        uint32_t it = 0;                 // the next iteration of this CTA to be counted
         uint32_t idle = 0;
-        FZ_PROF(long long pc_spread = 0; long long pc_pick = 0; long long pc_res = 0; long long pc_polls = 0; long long pc_tiles = 0; long long t_pick[D];)
-        while (nxt < n_tiles || n_pend != 0) {
+        FZ_PROF(long long pc_spread = 0; long long pc_pick = 0; long long pc_res = 0; long long pc_polls = 0; long long pc_tiles = 0; long long t_pick[D];
+                long long pc_poll_cyc = 0; long long pc_first_holes = 0; long long pc_first_q = 0; long long pc_first_age = 0; long long pc_firsts = 0;
+                uint32_t pc_last_polled = 0xffffffffu;)
+        while (true) {
+            const uint32_t nxt = gs->tile_id[it % GS];  // its tile, if there is one
+            if (nxt == 0xffffffffu && n_pend == 0) break;
             bool progress = false;
-            if (nxt < n_tiles && n_pend < uint32_t(D) && mbar_test(bar_counted + 8 * (it % D), (it / D) & 1u)) {
+            if (nxt != 0xffffffffu && n_pend < uint32_t(D) && mbar_test(bar_counted + 8 * (it % D), (it / D) & 1u)) {
                 // tile `nxt` is counted and its function published (by the last worker to finish): take it over
                 const uint32_t slot = it % D;
                 FzPending p;
                 const uint32_t tfl = gs->tf_flags[slot];
                 p.tf.id = tfl & 1u; p.tf.cst = (tfl >> 1) & 1u; p.tf.delta = (tfl >> 2) & 1u; p.starts = (tfl >> 3) & 1u;
                 p.tf.cnt0 = gs->tf_cnt[slot];
-                const uint32_t efl = gs->ex_flags[slot][lane & 15];
+                const uint32_t efl = gs->ex_flags[slot][lane];
                 p.ex.id = efl & 1u; p.ex.cst = (efl >> 1) & 1u; p.ex.delta = (efl >> 2) & 1u;
-                p.ex.cnt0 = gs->ex_cnt[slot][lane & 15];
-                p.cur = uint32_t(nxt); p.par = slot;
+                p.ex.cnt0 = gs->ex_cnt[slot][lane];
+                p.cur = nxt; p.par = slot;
                 FZ_PROF({ const long long now = clock64(); pc_spread += gs->t_pub[slot] - gs->t_first[slot]; pc_pick += now - gs->t_pub[slot];
                           for (int d = 0; d < D; ++d) if (uint32_t(d) == n_pend) t_pick[d] = gs->t_pub[slot]; ++pc_tiles; })
-                // the geometry of the tile D iterations on goes into the slot of the tile D iterations back, which every
-                // worker has emitted by now (it counted this one after that); the `resolved` arrive below releases it
-                if (lane == 0)
-                    fz_tile_geometry<C>(a, chunk, nxt + (unsigned long long)D * tile_step, n_tiles, g_ck, g_rem, last_ck, gs, (it + D) % (2 * D));
-                g_ck += step_ck;
-                g_rem += step_rem;
-                if (g_rem >= chunk) { g_rem -= chunk; ++g_ck; }
+                // claim the tile of iteration it+D+1; its slot was last read 2D iterations ago; the `resolved` arrive below
+                // releases it to the workers
+                if (lane == 0) fz_tile_geometry<C>(a, chunk, fz_claim(claim, n_tiles), n_tiles, last_ck, gs, (it + D + 1) % GS);
+                __syncwarp();
 #pragma unroll
                 for (int d = 0; d < D; ++d)
                     if (uint32_t(d) == n_pend) pend[d] = p;
                 ++n_pend;
-                nxt += tile_step;
                 ++it;
                 progress = true;
             }
             FZ_PROF(if (n_pend != 0) ++pc_polls;)
+            FZ_PROF(uint32_t ph = 0; uint32_t pq = 0; const long long tp0 = clock64(); const bool first_poll = n_pend != 0 && pend[0].cur != pc_last_polled;)
+#ifdef BLT_FUSED_PROF
+            const bool poll_ok = n_pend != 0 && fz_chain_poll<WG, C::LB>(a, gs, desc, pend[0], n_tiles, lane, &ph, &pq);
+            if (n_pend != 0) {
+                pc_poll_cyc += clock64() - tp0;
+                if (first_poll) { pc_first_holes += ph; pc_first_q += pq; pc_first_age += tp0 - t_pick[0]; ++pc_firsts; pc_last_polled = pend[0].cur; }
+            }
+            if (poll_ok) {
+#else
             if (n_pend != 0 && fz_chain_poll<WG, C::LB>(a, gs, desc, pend[0], n_tiles, lane)) {
+#endif
                 const uint32_t slot = pend[0].par;
                 FZ_PROF({ pc_res += clock64() - t_pick[0]; for (int d = 0; d + 1 < D; ++d) t_pick[d] = t_pick[d + 1]; })
                 __syncwarp();
@@ -502,8 +525,10 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             }
         }
         FZ_PROF(if (lane == 0 && blockIdx.x < 256) {
-            unsigned long long *pp = g_fz_prof + (size_t(blockIdx.x) * 16 + 15) * 8;
+            unsigned long long *pp = g_fz_prof + (size_t(blockIdx.x) * 32 + 31) * 8;
             pp[0] = pc_spread; pp[1] = pc_pick; pp[2] = pc_res; pp[3] = pc_polls; pp[4] = pc_tiles;
+            unsigned long long *pq2 = g_fz_prof + (size_t(blockIdx.x) * 32 + 30) * 8;
+            pq2[0] = pc_poll_cyc; pq2[1] = pc_first_holes; pq2[2] = pc_first_q; pq2[3] = pc_first_age; pq2[4] = pc_firsts;
         })
         return;
     }
@@ -516,7 +541,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     const uint32_t wbar = smem_u32(&gs->wbar[wg]);
     const uint32_t slice_off = uint32_t(wg * C::WARP_BYTES);
     uint32_t parity = 0;
-    if (tile0 < n_tiles) fz_warp_copy<C>(a, tile0, wg, slice, wbar, lane);
+    if (gs->tile_id[0] != 0xffffffffu) fz_warp_copy<C>(a, gs->tile_id[0], wg, slice, wbar, lane);
     // D sets of retained tiles: tokens and emit masks stay in registers until the tile's prefix is known.  Iteration
     // `it` counts into set it % D and emits the tile of iteration it - (D-1) from set (it + 1) % D.
     uint32_t hv[D][R][4], ov[D][R][4], em[D][R];
@@ -524,18 +549,17 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
 
     auto iteration = [&](auto ns_c, auto os_c, uint32_t it) -> bool {
         constexpr int NS = decltype(ns_c)::value, OS = decltype(os_c)::value;
-        const unsigned long long cur = (unsigned long long)tile0 + (unsigned long long)it * tile_step;
-        const bool have_new = cur < n_tiles;
-        const bool have_old = it >= uint32_t(D - 1) &&
-                              (unsigned long long)tile0 + (unsigned long long)(it - uint32_t(D - 1)) * tile_step < n_tiles;
+        const uint32_t cur = gs->tile_id[it % GS];
+        const bool have_new = cur != 0xffffffffu;
+        const bool have_old = it >= uint32_t(D - 1) && gs->tile_id[(it - uint32_t(D - 1)) % GS] != 0xffffffffu;
         if (!have_new && !have_old) return false;
         if (have_new) {
-            const uint32_t slot = it % D, gslot = it % (2 * D);
+            const uint32_t slot = it % D, gslot = it % GS;
             const uint32_t tile_len = gs->len[gslot];
             const uint32_t wall0 = gs->wall[gslot][0], wall1 = gs->wall[gslot][1];  // chunk-last elements in this tile, if any
             const bool full = tile_len == uint32_t(C::TILE);
             FZ_PROF(pf_t = clock64();)
-            if (!mbar_wait<20>(wbar, parity)) *a.scratch.overflow = 3u;
+            if (!mbar_wait<2000>(wbar, parity)) *a.scratch.overflow = 3u;
             parity ^= 1u;
             FZ_PROF({ const long long t1 = clock64(); pf_copy += t1 - pf_t; pf_t = t1; ++pf_tiles; })
             // ---- count: lookups (retained), run parity under carry_in = 0, the slice's carry function ----
@@ -588,7 +612,8 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 }
             }
             // every lane has read its share of the buffer: the slice of the next tile may land in it
-            if (cur + tile_step < n_tiles) fz_warp_copy<C>(a, uint32_t(cur + tile_step), wg, slice, wbar, lane);
+            const uint32_t nxt_tile = gs->tile_id[(it + 1) % GS];
+            if (nxt_tile != 0xffffffffu) fz_warp_copy<C>(a, nxt_tile, wg, slice, wbar, lane);
             else __syncwarp();
             uint32_t last = 0;
             if (lane == 0) {
@@ -605,7 +630,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 // detour through the chain warp: other CTAs' look-backs are waiting for it), then hands the tile over
                 __threadfence_block();
                 if (lane == 0) gs->arrived[slot] = 0u;
-                const FzPending p = fz_chain_publish<WG>(gs, desc, uint32_t(cur), gs->flags[gslot], slot, lane);
+                const FzPending p = fz_chain_publish<WG>(gs, desc, cur, gs->flags[gslot], slot, lane);
                 if (lane < WG) {
                     gs->ex_flags[slot][lane] = p.ex.id | (p.ex.cst << 1) | (p.ex.delta << 2);
                     gs->ex_cnt[slot][lane] = p.ex.cnt0;
@@ -624,21 +649,21 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         // ---- emit (D-1 tiles behind): compaction of the retained tokens of the whole slice, streamed out in words ----
         if (have_old) {
             const uint32_t jt = it - uint32_t(D - 1);
-            const uint32_t slot = jt % D, gslot = jt % (2 * D);
+            const uint32_t slot = jt % D, gslot = jt % GS;
             const uint32_t old_len = gs->len[gslot];
             const uint32_t old_wall0 = gs->wall[gslot][0], old_wall1 = gs->wall[gslot][1];
             const bool old_full = old_len == uint32_t(C::TILE);
             FZ_PROF(pf_t = clock64();)
-            if (!mbar_wait<100>(bar_resolved + 8 * slot, (jt / D) & 1u)) *a.scratch.overflow = 3u;
+            if (!mbar_wait<2000>(bar_resolved + 8 * slot, (jt / D) & 1u)) *a.scratch.overflow = 3u;
             FZ_PROF({ const long long t1 = clock64(); pf_chain += t1 - pf_t; pf_t = t1; })
             const unsigned long long rv = gs->res[slot][wg];
             const uint32_t slice_carry = uint32_t(rv >> 63);
             const unsigned long long rel0 = rv & ~R_CARRY;  // tokens of the launch in front of the slice
             const unsigned long long abs0 = rel0 + a.out_base_tokens;
-            // logical token 0 of the staging line corresponds to a.out[wpos], wpos is even; `head`: that slot belongs
-            // to the slice in front of this one (it holds nothing and is not written here)
-            const unsigned long long wpos = abs0 & ~1ull;
-            const uint32_t head = uint32_t(abs0 & 1ull);
+            // logical token 0 of the staging line corresponds to a.out[wpos], a 16-byte boundary of the output; the first
+            // `head` slots belong to the slice in front of this one (they hold nothing and are not written here)
+            const unsigned long long wpos = abs0 & ~7ull;
+            const uint32_t head = uint32_t(abs0 & 7ull);
             if (slice_carry != 0u) {
                 // the lanes in front of the slice's first non-identity segment see carry_in = 1 (the count assumed 0)
                 bool dep = true;
@@ -697,14 +722,18 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
 #pragma unroll
             for (int k = 0; k < R; ++k) { x_or |= em[OS][k] ^ 0x5555u; x_and &= em[OS][k] ^ 0x5555u; }
             const bool dense0 = __all_sync(FULL, x_or == 0u), dense1 = __all_sync(FULL, x_and == 0xFFFFu);
-            if (fits && (dense0 || dense1) && (abs0 & 7ull) == 0) {
+            if (fits && (dense0 || dense1) && head == 0u) {
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     const uint32_t *tv = dense0 ? hv[OS][k] : ov[OS][k];
                     stg_stream_v4(a.out + abs0 + size_t(k) * 256 + size_t(lane) * 8, make_uint4(tv[0], tv[1], tv[2], tv[3]));
                 }
             } else if (fits) {
-                // R independent chains of predicated 2-byte stores (position-major so that they interleave)
+                // R independent chains of 2-byte stores (position-major so that they interleave).  The stores are NOT
+                // predicated: the token of a position that emits nothing lands in the slot of the lane's next emitting
+                // position (no two neighbours are both silent) and is overwritten by it; only position 15, whose
+                // successor belongs to the next lane, is predicated.  Silent positions behind the end of the input pile
+                // up in the scratch slot behind the last token.  (The cursor bump is a multiply-high-add: fma pipe.)
                 uint32_t sp[R];
 #pragma unroll
                 for (int k = 0; k < R; ++k) sp[k] = stage_s + 2u * (head + pos[k]);
@@ -713,42 +742,55 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         const uint32_t v = (j & 1) ? ov[OS][k][j >> 2] : hv[OS][k][j >> 2];
-                        const uint32_t tok = ((j >> 1) & 1) ? (v >> 16) : v;
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                            "setp.ne.u32 p, %2, 0;\n\t"
-                            "mul.hi.u32 t, %0, 0x08000000;\n\t"
-                            "and.b32 t, t, 0x1C;\n\t"
-                            "xor.b32 t, t, %0;\n\t"
-                            "@p st.shared.u16 [t], %1;\n\t"
-                            "@p mad.lo.u32 %0, %0, 1, 2;\n\t}"
-                            : "+r"(sp[k])
-                            : "h"(uint16_t(tok)), "r"(em[OS][k] & (1u << j))
-                            : "memory");
+                        const uint32_t tok = ((j >> 1) & 1) ? shr_fma(v, 1u << 16) : v;
+                        const uint32_t bit = em[OS][k] & (1u << j);
+                        uint32_t phys;
+                        asm("{\n\t.reg .b32 t;\n\t"
+                            "mul.hi.u32 t, %1, 0x20000000;\n\t"
+                            "and.b32 t, t, 0x70;\n\t"
+                            "xor.b32 %0, t, %1;\n\t}"
+                            : "=r"(phys)
+                            : "r"(sp[k]));
+                        if (j < 15) {
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(phys), "h"(uint16_t(tok)) : "memory");
+                            if (j == 0) asm("mad.lo.u32 %0, %1, 2, %0;" : "+r"(sp[k]) : "r"(bit));
+                            else if (j == 1) sp[k] += bit;
+                            else asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(sp[k]) : "r"(bit), "r"(1u << (33 - j)));
+                        } else {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.u32 p, %2, 0;\n\t"
+                                "@p st.shared.u16 [%0], %1;\n\t}" ::"r"(phys), "h"(uint16_t(tok)), "r"(bit)
+                                : "memory");
+                        }
                     }
                 }
                 __syncwarp();
-                // tokens head .. total-1 of the line go to a.out[wpos + head ...]: whole words, then the odd last token
-                const uint32_t total = head + have;
-                const uint32_t nw = total >> 1;
+                // tokens head .. head+have-1 of the line go to a.out[wpos + head ...]: whole 16-byte vectors, and the
+                // tokens of the two partial vectors at the ends one by one (lanes 0-7: first vector, lanes 8-15: last)
+                const uint32_t end = head + have;
+                const uint32_t v_first = head != 0u ? 1u : 0u, v_end = end >> 3;
                 unsigned char *gout = reinterpret_cast<unsigned char *>(a.out + wpos);
-                // word v = lane + 32 i sits in window i of the line: its bank bits are XORed with (window index) & 7
-                const uint32_t lane4 = uint32_t(lane) << 2;
-                const uint32_t w7 = stage_s >> 7;
-                if (uint32_t(lane) < nw) {
-                    const uint32_t word = lds_u32(stage_s + (lane4 ^ ((w7 & 7u) << 2)));
-                    if (lane == 0 && head != 0) *reinterpret_cast<uint16_t *>(gout + 2) = uint16_t(word >> 16);
-                    else stg_stream_u32(gout + lane4, word);
+                {
+                    const uint32_t L = lane < 8 ? uint32_t(lane) : (8u * v_end + uint32_t(lane) - 8u);
+                    const bool mine = lane < 8 ? (head != 0u && L >= head && L < end) : (lane < 16 && L >= head && L < end);
+                    if (mine) {
+                        uint32_t tv;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(tv) : "r"(stage_swz(stage_s + 2u * L)) : "memory");
+                        *reinterpret_cast<uint16_t *>(gout + 2u * L) = uint16_t(tv);
+                    }
                 }
-#pragma unroll 4
-                for (uint32_t i = 1; i * 32u < nw; ++i) {  // warp-uniform trip count
-                    const uint32_t word = lds_u32(stage_s + i * 128u + (lane4 ^ (((w7 + i) & 7u) << 2)));
-                    if (i * 32u + uint32_t(lane) < nw) stg_stream_u32(gout + i * 128u + lane4, word);
-                }
-                if ((total & 1u) && total - 1u >= head && !(total == 1u && head == 1u) && lane == 0) {
-                    uint32_t lastv;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lastv) : "r"(stage_swz(stage_s + 2u * (total - 1u))) : "memory");
-                    *reinterpret_cast<uint16_t *>(gout + 2u * (total - 1u)) = uint16_t(lastv);
+#pragma unroll 2
+                for (uint32_t v0 = 0; v0 < v_end; v0 += 32u) {  // warp-uniform trip count
+                    const uint32_t v = v0 + uint32_t(lane);
+                    if (v >= v_first && v < v_end) {
+                        uint4 q;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                                     : "r"(stage_swz(stage_s + 16u * v))
+                                     : "memory");
+                        stg_stream_v4(gout + 16u * v, q);
+                    }
                 }
                 __syncwarp();
             }
@@ -766,7 +808,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         }
     }
     FZ_PROF(if (lane == 0 && blockIdx.x < 256) {
-        unsigned long long *pp = g_fz_prof + (size_t(blockIdx.x) * 16 + wg) * 8;
+        unsigned long long *pp = g_fz_prof + (size_t(blockIdx.x) * 32 + wg) * 8;
         uint32_t smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         pp[0] = pf_copy; pp[1] = pf_count; pp[2] = pf_chain; pp[3] = pf_emit; pp[4] = pf_tiles; pp[5] = smid;

@@ -535,7 +535,7 @@ cudaError_t launch_fill_chunk_ends(uint64_t *d_ends, size_t n, size_t chunk, uns
     return cudaGetLastError();
 }
 
-static const char *kVariantNames[] = {"r4", "r8", "walk", "fused 15x4 d2", "fused 15x2 d4"};
+static const char *kVariantNames[] = {"r4", "r8", "walk", "fused 15x4 d2", "fused 23x2 d2"};
 int num_sweep_variants() { return int(sizeof(kVariantNames) / sizeof(kVariantNames[0])); }
 const char *sweep_variant_name(int v) { return (v >= 0 && v < num_sweep_variants()) ? kVariantNames[v] : "?"; }
 
@@ -581,9 +581,9 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, 
         if (host_launches) *host_launches = kLaunchesFused;
         return FusedLaunch<15, 4, 2>::launch(a, d_table, stream);
     }
-    if (variant == 4 && FusedLaunch<15, 2, 4>::applicable(a)) {
+    if (variant == 4 && FusedLaunch<23, 2, 2>::applicable(a)) {
         if (host_launches) *host_launches = kLaunchesFused;
-        return FusedLaunch<15, 2, 4>::launch(a, d_table, stream);
+        return FusedLaunch<23, 2, 2>::launch(a, d_table, stream);
     }
     if (host_launches) *host_launches = kLaunchesExact;
     switch (variant) {

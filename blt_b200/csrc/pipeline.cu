@@ -2,9 +2,10 @@
 // file-to-file form (blt_run_tokenizer) of run_mmap_pipeline / run_stream_pipeline
 // (blt_core/src/pipeline.rs:56-240).  Chunks are cut at fixed offsets k*C from the start of the input
 // (pipeline.rs:73-81), flow through S slots (H2D copy stream -> compute stream -> D2H copy stream)
-// and are written strictly in chunk order (pipeline.rs:153-168).  With several GPUs each device gets
-// a contiguous range of chunks and its own pipeline; the only cross-GPU datum is each range's output
-// length (a host-side prefix), so nothing is exchanged between devices.
+// and are written strictly in chunk order (pipeline.rs:153-168).  With several GPUs the chunks are dealt
+// round-robin (chunk k -> GPU k mod G, blt_file_chunk_device) and each device runs its own pipeline; the
+// only cross-GPU datum is each chunk's output length (a host-side prefix), so nothing is exchanged
+// between devices.
 #include "pipeline.h"
 
 #include <algorithm>
@@ -482,19 +483,31 @@ struct OffsetBoard {
 #endif
 class OutPrealloc {
   public:
+    enum State { READY = 0, NO_SPACE = 1, UNSUPPORTED = 2 };
     ~OutPrealloc() { finish(); }
     void start(int fd, uint8_t *map, uint64_t bound, uint64_t sure) {
         fd_ = fd; map_ = map; bound_ = bound;
         want_.store(std::min(sure, bound));
+        running_ = true;
         th_ = std::thread([this] { loop(); });
     }
-    // the writers have reached `written`; keep `ahead` more bytes ready
-    void advance(uint64_t written, uint64_t ahead) {
-        uint64_t lo = low_.load(std::memory_order_relaxed);
-        while (lo < written && !low_.compare_exchange_weak(lo, written, std::memory_order_relaxed)) {}
-        const uint64_t w = std::min(bound_, written + ahead);
+    bool running() const { return running_; }
+    // A writer is about to store [off, off+len) into the mapping: asks for the pages (and `ahead` more) and waits
+    // until they exist.  A store into a page of the sparse mapping that cannot be allocated (tmpfs full, quota)
+    // would raise SIGBUS and kill the process; the reference returns an io::Error there, and so does this:
+    // NO_SPACE -> the caller fails with BLT_ERR_IO; UNSUPPORTED (no fallocate on this filesystem) -> the caller
+    // writes that range with pwrite(), which reports ENOSPC itself.
+    State ensure(uint64_t off, uint64_t len, uint64_t ahead, int *os_errno) {
+        const uint64_t need = std::min(bound_, off + len);
+        const uint64_t w = std::min(bound_, off + len + ahead);
         uint64_t cur = want_.load(std::memory_order_relaxed);
         while (cur < w && !want_.compare_exchange_weak(cur, w, std::memory_order_relaxed)) {}
+        for (;;) {
+            if (done_.load(std::memory_order_acquire) >= need) return READY;
+            const int st = state_.load(std::memory_order_acquire);
+            if (st != READY) { *os_errno = errno_.load(); return State(st); }
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
     }
     void finish() {
         stop_.store(true);
@@ -507,21 +520,26 @@ class OutPrealloc {
         constexpr uint64_t kPiece = uint64_t(32) << 20;
         uint64_t done = 0;
         while (!stop_.load(std::memory_order_relaxed) && done < bound_) {
-            const uint64_t lo = low_.load(std::memory_order_relaxed) & ~(kPiece - 1);
-            if (done < lo) done = lo;  // the writers overtook us: do not redo what they faulted in themselves
             const uint64_t w = want_.load(std::memory_order_relaxed);
-            if (done >= w) { std::this_thread::sleep_for(std::chrono::microseconds(200)); continue; }
+            if (done >= w) { std::this_thread::sleep_for(std::chrono::microseconds(100)); continue; }
             const uint64_t len = std::min(kPiece, bound_ - done);
-            if (fallocate(fd_, 0, off_t(done), off_t(len)) != 0) return;
+            if (fallocate(fd_, 0, off_t(done), off_t(len)) != 0) {
+                const int e = errno;
+                errno_.store(e);
+                state_.store((e == ENOSPC || e == EDQUOT || e == EFBIG) ? NO_SPACE : UNSUPPORTED, std::memory_order_release);
+                return;
+            }
             (void)madvise(map_ + done, size_t((len + 4095) & ~uint64_t(4095)), MADV_POPULATE_WRITE);  // best effort
             done += len;
-            done_.store(done, std::memory_order_relaxed);
+            done_.store(done, std::memory_order_release);
         }
     }
     int fd_ = -1;
     uint8_t *map_ = nullptr;
     uint64_t bound_ = 0;
-    std::atomic<uint64_t> want_{0}, low_{0}, done_{0};
+    bool running_ = false;
+    std::atomic<uint64_t> want_{0}, done_{0};
+    std::atomic<int> state_{READY}, errno_{0};
     std::atomic<bool> stop_{false};
     std::thread th_;
 };
@@ -597,6 +615,17 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
             if (p == MAP_FAILED) { close(in_fd); return fail(BLT_ERR_IO, std::string("mmap failed: ") + std::strerror(errno)); }
             map = static_cast<const uint8_t *>(p);
             madvise(p, n, MADV_SEQUENTIAL);
+        }
+    }
+    // No device, no work: checked BEFORE the output is created and truncated, so that a failure does not clobber an
+    // existing output file (passthrough is a host copy and needs no device).
+    int n_dev = 0;
+    if (!cfg->passthrough) {
+        const int drc = blt_device_count(&n_dev);
+        if (drc) {
+            if (map) munmap(const_cast<uint8_t *>(map), n);
+            if (in_is_file) close(in_fd);
+            return drc;  // no CPU fallback
         }
     }
     OutFile of;
@@ -685,10 +714,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
     };
 
     slog.mark("config parsed, io open");
-    int n_dev = 0;
-    int rc = blt_device_count(&n_dev);
-    slog.mark("device count");
-    if (rc) { cleanup(); return rc; }  // no CPU fallback
+    int rc = BLT_OK;
     // default: one GPU.  The host side (page cache, PCIe) bounds file-to-file long before one B200 does, and
     // every further context costs about a second of start-up (host pipeline).
     int n_gpus = cfg->num_gpus > 0 ? std::min(cfg->num_gpus, n_dev) : 1;
@@ -768,9 +794,33 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
             });
         };
         auto put = [&](const uint8_t *buf, size_t len, uint64_t off) -> int {
-            if (of.map) {  // mapped output: plain stores, split over the helper threads
+            if (of.map) {  // mapped output: plain stores, split over the helper threads, into pages that exist
                 if (off + len > of.map_len) return fail(BLT_ERR_CAPACITY, "output exceeds its upper bound");
-                par_memcpy(of.map + off, buf, len);
+                int e = 0;
+                OutPrealloc::State st = OutPrealloc::UNSUPPORTED;
+                if (pre.running()) {
+                    st = pre.ensure(off, len, uint64_t(1) << 30, &e);
+                } else if (fallocate(of.fd, 0, off_t(off), off_t(len)) == 0) {  // BLT_NO_PREALLOC: the writer allocates its own range
+                    st = OutPrealloc::READY;
+                } else {
+                    e = errno;
+                    if (e == ENOSPC || e == EDQUOT || e == EFBIG) st = OutPrealloc::NO_SPACE;
+                }
+                if (st == OutPrealloc::NO_SPACE)
+                    return fail(BLT_ERR_IO, std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")");
+                if (st == OutPrealloc::READY) {
+                    par_memcpy(of.map + off, buf, len);
+                    return BLT_OK;
+                }
+                // no fallocate on this filesystem: pwrite reports a full device as an error instead of a SIGBUS
+                while (len) {
+                    const ssize_t w = pwrite(of.fd, buf, len, off_t(off));
+                    if (w < 0) {
+                        if (errno == EINTR) continue;
+                        return fail(BLT_ERR_IO, std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
+                    }
+                    buf += w; len -= size_t(w); off += uint64_t(w);
+                }
                 return BLT_OK;
             }
             return of.write_at(buf, len, off);
@@ -781,6 +831,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(now() - a).count(); };
         if (rc == BLT_OK) {
             ChunkSource src;
+            // the chunks k with blt_file_chunk_device(k, n_gpus) == g
             src.n = n; src.chunk = chunk; src.first = g; src.stride = size_t(n_gpus);
             src.count = (n_chunks > g) ? (n_chunks - g + size_t(n_gpus) - 1) / size_t(n_gpus) : 0;
             pipe = ctx->acquire();
@@ -799,7 +850,6 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
                 t0 = now();
                 const int w = put(p.sl->h_out, p.len, prefix + uint64_t(base));
                 t_out += since(t0);
-                pre.advance(prefix + uint64_t(base) + p.len, uint64_t(1) << 30);
                 produced += p.len;
                 p.sl = nullptr;
                 return w;

@@ -175,7 +175,10 @@ typedef struct blt_core_config {
 
 /* run_tokenizer(CoreConfig::new_from_cli(...)) (lib.rs:149-174, 245-267): parse + load merges, pick
  * the strategy, size chunks, open input (mmap) / output, write the content-type prefix, run the
- * chunk pipeline with chunks sharded contiguously over the GPUs, write results in chunk order. */
+ * chunk pipeline, write results in chunk order.  With num_gpus = G > 1 the chunks are dealt ROUND-ROBIN: chunk k is
+ * processed by GPU blt_file_chunk_device(k, G) = k mod G, each GPU with its own pipeline; the G pipelines advance
+ * through the file together, so chunk k's file offset (the sum of the output lengths of chunks 0..k-1, kept on a
+ * host-side board) is known almost as soon as its own bytes are back.  Nothing is exchanged between devices. */
 BLT_API int blt_run_tokenizer(const blt_core_config *cfg);
 /* The inverse, file to file (no reference counterpart): `input` holds big-endian u16 tokens, `output`
  * receives the bytes; merges_file / passthrough select the table as above; content_type != NONE means the
@@ -199,9 +202,13 @@ BLT_API size_t blt_effective_chunk_size(int has_cli, size_t cli_size, size_t thr
 BLT_API size_t blt_determine_thread_count(int has_override, size_t override_val);
 /* ContentType::get_token_value (lib.rs:96-103); 0 for BLT_CONTENT_NONE. */
 BLT_API uint16_t blt_content_type_token(int content_type);
-/* Chunk k of K goes to GPU floor(k*G/K) (contiguous ranges): writes the first
- * chunk index of each of the G+1 range bounds into bounds[0..G]. */
+/* Contiguous partition for callers that give every GPU (or rank) its OWN output, e.g. one process per GPU:
+ * chunk k of K goes to GPU floor(k*G/K); writes the first chunk index of each of the G+1
+ * range bounds into bounds[0..G].  blt_run_tokenizer, whose GPUs share ONE ordered output file, does not use it
+ * (see blt_file_chunk_device). */
 BLT_API void blt_shard_chunks(size_t n_chunks, int n_gpus, size_t *bounds);
+/* The device that blt_run_tokenizer gives chunk k when it runs on n_gpus devices: k mod n_gpus. */
+BLT_API int blt_file_chunk_device(size_t chunk_index, int n_gpus);
 
 #ifdef __cplusplus
 }

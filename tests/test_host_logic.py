@@ -133,6 +133,16 @@ def test_shard_chunks_is_floor_k_g_over_k():
                 assert b[owner] <= k < b[owner + 1]
 
 
+def test_file_pipeline_deals_chunks_round_robin():
+    """blt_run_tokenizer's sharding (include/blt_cuda.h): chunk k -> GPU k mod G; every GPU gets floor or ceil of K/G chunks."""
+    for g in [1, 2, 3, 4, 8]:
+        owners = [nat.file_chunk_device(k, g) for k in range(67)]
+        assert owners == [k % g for k in range(67)]
+        counts = [owners.count(d) for d in range(g)]
+        assert max(counts) - min(counts) <= 1
+    assert nat.file_chunk_device(5, 0) == 0
+
+
 # ---- Python surface, mirroring blt_python/tests/test_tokenizer.py (the rows that need no device) ----
 
 def test_python_surface_shape():

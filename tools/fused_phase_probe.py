@@ -27,14 +27,20 @@ for cfg in (2, 3):
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
         s.process_resident(d_in.data_ptr(), n, chunk, d_out.data_ptr(), 2 * n, 0, st, sync=True)
-    buf = np.zeros(256 * 16 * 8, dtype=np.uint64)
+    buf = np.zeros(256 * 32 * 8, dtype=np.uint64)
     assert nat.lib().blt_debug_fused_profile(buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size)) == 0
-    ch = buf.reshape(256, 16, 8).astype(np.float64)[:148, 15]
+    ch = buf.reshape(256, 32, 8).astype(np.float64)[:148, 31]
+    c2 = buf.reshape(256, 32, 8).astype(np.float64)[:148, 30]
     print(json.dumps({"config": cfg, "chain_warp_per_tile": {"first_to_last_worker_cycles": round(float((ch[:, 0] / ch[:, 4]).mean())),
                       "publish_to_pickup_cycles": round(float((ch[:, 1] / ch[:, 4]).mean())),
                       "publish_to_resolved_cycles": round(float((ch[:, 2] / ch[:, 4]).mean())),
-                      "polls": round(float((ch[:, 3] / ch[:, 4]).mean()), 2)}}), flush=True)
-    p = buf.reshape(256, 16, 8).astype(np.float64)[:148, :15]
+                      "polls": round(float((ch[:, 3] / ch[:, 4]).mean()), 2),
+                      "cycles_per_poll": round(float((c2[:, 0] / ch[:, 3]).mean())),
+                      "first_poll_unpublished_tiles": round(float((c2[:, 1] / c2[:, 4]).mean()), 2),
+                      "first_poll_distance_to_prefix": round(float((c2[:, 2] / c2[:, 4]).mean()), 1),
+                      "first_poll_cycles_after_publish": round(float((c2[:, 3] / c2[:, 4]).mean()))}}), flush=True)
+    W = 15 if os.environ["BLT_SWEEP_VARIANT"] == "3" else 23
+    p = buf.reshape(256, 32, 8).astype(np.float64)[:148, :W]
     tot = p[:, :, 0:4].sum(axis=2)
     frac = p[:, :, 0:4] / tot[:, :, None]
     print(json.dumps({"config": cfg, "mean_frac_copywait_count_chainwait_emit": [round(float(x), 4) for x in frac.mean(axis=(0, 1))],

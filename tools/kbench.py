@@ -15,7 +15,7 @@ import torch  # noqa: E402
 
 from blt_b200 import _native as nat, synth  # noqa: E402
 
-VARIANT_NAMES = ["exact r4", "exact r8", "exact walk", "fused 15x4 d2", "fused 15x2 d4"]
+VARIANT_NAMES = ["exact r4", "exact r8", "exact walk", "fused 15x4 d2", "fused 23x2 d2"]
 
 
 def time_resident(strat, d_in, n, chunk, d_out, iters):
