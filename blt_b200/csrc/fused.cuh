@@ -106,6 +106,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // one instruction per wake-up instead of spinning through the issue slots and the alu pipe of the working ones.
 template <int HINT_NS>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
     for (uint32_t tries = 0; tries < (1u << 22); ++tries) {
         uint32_t ok;
         asm volatile(
@@ -156,7 +157,12 @@ __device__ __forceinline__ uint32_t lds_tbl(uint32_t addr) {
 // 128-byte window (address bits 4-6) is XORed with the index of the window (mod 8), so that the lanes' 2-byte stores
 // (one lane's tokens about 17 bytes behind the other's) do not pile up on a few banks while 16-byte vectors stay whole
 // for the flush.  Every 128-byte window is permuted within itself: lines are whole, 128-byte aligned windows.
-__device__ __forceinline__ uint32_t stage_swz(uint32_t addr) { return addr ^ ((addr >> 3) & 0x70u); }
+#ifdef BLT_FZ_STAGE_SWIZZLE
+constexpr bool kStageSwizzle = true;
+#else
+constexpr bool kStageSwizzle = false;  // measured: the swizzle costs 2 instructions per position and does not pay (r2p kbench)
+#endif
+__device__ __forceinline__ uint32_t stage_swz(uint32_t addr) { return kStageSwizzle ? (addr ^ ((addr >> 3) & 0x70u)) : addr; }
 
 // The SEG/2 pairs of one 16-byte segment that start at positions of parity PAR: the big-endian u16 to emit at each of
 // those positions (merged id if the pair is a rule, else the element itself), two per register in position order.
@@ -744,13 +750,14 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                         const uint32_t v = (j & 1) ? ov[OS][k][j >> 2] : hv[OS][k][j >> 2];
                         const uint32_t tok = ((j >> 1) & 1) ? shr_fma(v, 1u << 16) : v;
                         const uint32_t bit = em[OS][k] & (1u << j);
-                        uint32_t phys;
-                        asm("{\n\t.reg .b32 t;\n\t"
-                            "mul.hi.u32 t, %1, 0x20000000;\n\t"
-                            "and.b32 t, t, 0x70;\n\t"
-                            "xor.b32 %0, t, %1;\n\t}"
-                            : "=r"(phys)
-                            : "r"(sp[k]));
+                        uint32_t phys = sp[k];
+                        if (kStageSwizzle)
+                            asm("{\n\t.reg .b32 t;\n\t"
+                                "mul.hi.u32 t, %1, 0x20000000;\n\t"
+                                "and.b32 t, t, 0x70;\n\t"
+                                "xor.b32 %0, t, %1;\n\t}"
+                                : "=r"(phys)
+                                : "r"(sp[k]));
                         if (j < 15) {
                             asm volatile("st.shared.u16 [%0], %1;" ::"r"(phys), "h"(uint16_t(tok)) : "memory");
                             if (j == 0) asm("mad.lo.u32 %0, %1, 2, %0;" : "+r"(sp[k]) : "r"(bit));

@@ -4,12 +4,16 @@
 // "the k most frequent adjacent byte pairs" of a sample, which needs exactly this histogram:
 // counts[b0 << 8 | b1] = number of i with in[i] = b0, in[i+1] = b1.
 // One persistent CTA per SM keeps all 65 536 counters in shared memory as u16 (128 KiB), bumped with 32-bit
-// shared-memory atomics on the containing word; after at most 49 152 positions (so no counter can wrap) the
-// CTA adds its non-zero counters to the global u64 histogram and clears them.  Every position is read once.
+// shared-memory atomics on the containing word.  The atomic returns the old word: a lane that sees its counter at
+// 16 384 or more raises a flag, the CTA looks at the flag every two rounds (32 768 positions, so a counter that was
+// below 16 384 at the last look cannot wrap before the next one) and only then adds its non-zero counters to the
+// global u64 histogram and clears them: uniform data never flushes before the end (a flush there is 65 536 global
+// atomics), text flushes when its hottest pair gets there.  Every position is read once.
 // Included by kernels.cu inside its anonymous namespace.
 #pragma once
 
-constexpr int kHistRoundsPerFlush = 3;  // 3 rounds x 1024 threads x 16 positions = 49 152 < 65 536
+constexpr int kHistRoundsPerLook = 2;      // 2 rounds x 1024 threads x 16 positions = 32 768
+constexpr uint32_t kHistFlushAt = 16384u;  // 16 383 + 32 768 + 16 384 < 65 536
 
 __global__ void __launch_bounds__(kCtaThreads, 1)
 pair_hist_kernel(const unsigned char *__restrict__ in, unsigned long long n, unsigned long long *__restrict__ counts) {
@@ -22,7 +26,9 @@ pair_hist_kernel(const unsigned char *__restrict__ in, unsigned long long n, uns
     const unsigned long long cta_span = (unsigned long long)kCtaThreads * 16;     // positions per CTA-round
     unsigned long long round = blockIdx.x;
     const unsigned long long n_rounds = (n_pairs + cta_span - 1) / cta_span;
-    int since_flush = 0;
+    int since_look = 0;
+    bool dirty = false;
+    uint32_t hot = 0;  // this lane saw a counter at kHistFlushAt or more
     auto flush = [&]() {
         __syncthreads();
         for (int i = threadIdx.x; i < 8192; i += blockDim.x) {
@@ -60,11 +66,18 @@ pair_hist_kernel(const unsigned char *__restrict__ in, unsigned long long n, uns
             // bytes j and j+1 of the lane's window
             const uint32_t lo = __funnelshift_r(words[j >> 2], words[(j >> 2) + 1], 8 * (j & 3));
             const uint32_t key = ((lo & 0xffu) << 8) | ((lo >> 8) & 0xffu);          // b0 << 8 | b1
-            if (uint32_t(j) < valid) atomicAdd(hist + (key >> 1), 1u << (16 * (key & 1u)));
+            if (uint32_t(j) < valid) {
+                const uint32_t old = atomicAdd(hist + (key >> 1), 1u << (16 * (key & 1u)));
+                hot |= ((old >> (16 * (key & 1u))) & 0xffffu) >= kHistFlushAt ? 1u : 0u;
+            }
         }
-        if (++since_flush == kHistRoundsPerFlush) { flush(); since_flush = 0; }
+        dirty = true;
+        if (++since_look == kHistRoundsPerLook) {
+            since_look = 0;
+            if (__syncthreads_or(int(hot))) { flush(); hot = 0; dirty = false; }
+        }
     }
-    if (since_flush) flush();
+    if (dirty) flush();
 }
 
 cudaError_t launch_pair_hist_impl(const unsigned char *d_in, size_t n, unsigned long long *d_counts, bool zero_first,

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fcntl.h>
 #include <functional>
 #include <sys/mman.h>
@@ -91,6 +92,8 @@ void Pipe::release() {
         if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
     }
     slots.clear();
+    for (cudaEvent_t e : piece_ev) cudaEventDestroy(e);
+    piece_ev.clear();
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_comp) cudaStreamDestroy(s_comp);
     if (s_d2h) cudaStreamDestroy(s_d2h);
@@ -274,12 +277,81 @@ int run_slots(blt_strategy *s, Pipe &pipe, const ChunkSource &src, Fetch fetch, 
     return BLT_OK;
 }
 
+// ONE unit through pageable caller buffers (blt_process_chunk as the reference's workers call it: a slice of an
+// mmap in, a fresh Vec<u8> out).  The unit is moved in pieces so that the host-side staging copies run beside
+// the DMA in both directions:  memcpy(piece i) || H2D(piece i-1)  ->  kernel(s) on the whole unit  ->
+// D2H(piece i+1) || memcpy(piece i).  The kernel needs the whole unit (run parity crosses pieces), so it sits
+// between the two pipelines; at 3 TB/s it is the smallest term.
+int run_one_unit_pieced(blt_strategy *s, Pipe &pipe, const ChunkSource &src, const uint8_t *in, uint8_t *out, size_t out_cap,
+                        size_t off, bool stage_in, bool stage_out, size_t *out_len) {
+    constexpr size_t kPiece = size_t(4) << 20;
+    Slot &sl = pipe.slots[0];
+    const size_t id = src.id_of(0);
+    const size_t len_in = src.len_of(id);
+    const uint8_t *base = in + src.off_of(id);
+    sl.in_len = len_in;
+    for (size_t o = 0; o < len_in; o += kPiece) {
+        const size_t l = std::min(kPiece, len_in - o);
+        const uint8_t *h = base + o;
+        if (stage_in) {
+            shared_par_memcpy(sl.h_in + o, base + o, l);
+            h = sl.h_in + o;
+        }
+        CUDA_TRY(cudaMemcpyAsync(sl.d_in + o, h, l, cudaMemcpyHostToDevice, pipe.s_h2d));
+    }
+    CUDA_TRY(cudaEventRecord(sl.ev_h2d, pipe.s_h2d));
+    CUDA_TRY(cudaStreamWaitEvent(pipe.s_comp, sl.ev_h2d, 0));
+    int rc = src.detok ? run_detok(s, pipe.ws, sl.d_in, sl.in_len, sl.d_out, 2 * pipe.cap, pipe.s_comp, &sl.res)
+                       : run_device(s, pipe.ws, sl.d_in, sl.in_len, src.wall, sl.d_out, 2 * pipe.cap, nullptr, pipe.s_comp, &sl.res);
+    if (rc) return rc;
+    if (sl.res.kind == DeviceResult::IN_SCRATCH)
+        CUDA_TRY(cudaMemcpyAsync(sl.h_ctrl, pipe.ws.scratch.ctrl, 32, cudaMemcpyDeviceToHost, pipe.s_comp));
+    CUDA_TRY(cudaEventRecord(sl.ev_done, pipe.s_comp));
+    CUDA_TRY(cudaEventSynchronize(sl.ev_done));
+    if (sl.res.kind == DeviceResult::IN_SCRATCH) {
+        rc = decode_ctrl(sl.h_ctrl, &sl.res);
+        if (rc) return rc;
+    }
+    const size_t len = sl.res.len;
+    if (off + len > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+    const size_t n_pieces = (len + kPiece - 1) / kPiece;
+    while (pipe.piece_ev.size() < n_pieces) {
+        cudaEvent_t e = nullptr;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        pipe.piece_ev.push_back(e);
+    }
+    for (size_t i = 0; i < n_pieces; ++i) {
+        const size_t o = i * kPiece, l = std::min(kPiece, len - o);
+        CUDA_TRY(cudaMemcpyAsync(stage_out ? sl.h_out + o : out + off + o, sl.d_out + o, l, cudaMemcpyDeviceToHost, pipe.s_d2h));
+        CUDA_TRY(cudaEventRecord(pipe.piece_ev[i], pipe.s_d2h));
+    }
+    for (size_t i = 0; i < n_pieces; ++i) {
+        CUDA_TRY(cudaEventSynchronize(pipe.piece_ev[i]));
+        const size_t o = i * kPiece, l = std::min(kPiece, len - o);
+        if (stage_out) shared_par_memcpy(out + off + o, sl.h_out + o, l);
+    }
+    *out_len = off + len;
+    return BLT_OK;
+}
+
 // Runs the units of `src` through a leased pipe: host `in` -> device -> host `out` (appended from byte `off`).
 // stage_in / stage_out: that side is pageable and goes through the pipe's pinned slots.
 int run_host_units(blt_strategy *s, const ChunkSource &src, const uint8_t *in, uint8_t *out, size_t out_cap, size_t off,
                    size_t unit_cap, bool stage_in, bool stage_out, size_t *out_len) {
     auto pipe = s->ctx->acquire();
     int rc = pipe->ensure(unit_cap, std::min(kSlots, src.count), stage_in || stage_out);
+    if (rc == BLT_OK && src.count == 1 && (stage_in || stage_out)) {
+        size_t total = off;
+        rc = run_one_unit_pieced(s, *pipe, src, in, out, out_cap, off, stage_in, stage_out, &total);
+        if (rc != BLT_OK) {
+            cudaStreamSynchronize(pipe->s_h2d);
+            cudaStreamSynchronize(pipe->s_comp);
+            cudaStreamSynchronize(pipe->s_d2h);
+        }
+        s->ctx->give_back(std::move(pipe));
+        if (rc == BLT_OK) *out_len = total;
+        return rc;
+    }
     // staged output is handed over one unit late, so that its D2H overlaps the next unit's staging
     struct Pending { Slot *sl = nullptr; size_t len = 0, at = 0; } pend;
     auto hand_over = [&](Pending &p) -> int {
@@ -544,6 +616,25 @@ class OutPrealloc {
     std::thread th_;
 };
 
+// blt_run_tokenizer is called once per file; in a long-lived process (the Python binding, a service, bench.py) the
+// device-side resources of one call are what the next call needs: contexts are kept per device for the life of the
+// process and their pipes (pinned staging slots: cudaHostAlloc runs at about 1 GB/s, 144 MiB per pipe) go back to
+// the context's pool instead of being freed.  The CLI makes one call and exits, so it frees nothing either.
+blt_ctx *file_ctx_for(int device, int *rc_out) {
+    static std::mutex mu;
+    static std::vector<blt_ctx *> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() <= size_t(device)) cache.resize(size_t(device) + 1, nullptr);
+    if (!cache[size_t(device)]) {
+        blt_ctx *c = nullptr;
+        *rc_out = blt_ctx_create(device, &c);
+        if (*rc_out != BLT_OK) return nullptr;
+        cache[size_t(device)] = c;
+    }
+    *rc_out = BLT_OK;
+    return cache[size_t(device)];
+}
+
 int build_like(blt_ctx *ctx, const blt_strategy *proto, blt_strategy **out) {
     switch (proto->mode) {
         case Mode::Basic: return blt_strategy_basic(ctx, out);
@@ -777,14 +868,19 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
         blt_ctx *ctx = nullptr;
         blt_strategy *st = nullptr;
         std::unique_ptr<Pipe> pipe;
-        int rc = blt_ctx_create(sh.device, &ctx);
-        slog.mark("context created", sh.device);
+        int rc = BLT_OK;
+        ctx = file_ctx_for(sh.device, &rc);
+        if (rc == BLT_OK && cudaSetDevice(sh.device) != cudaSuccess) rc = fail(BLT_ERR_CUDA, "cudaSetDevice failed");
+        slog.mark("context ready", sh.device);
         if (rc == BLT_OK) rc = build_like(ctx, &proto, &st);
         slog.mark("strategy built", sh.device);
-        // host copies are split over `--threads / gpus` threads (at most 8), like the reference's workers
-        HostPool io(std::min<size_t>(8, std::max<size_t>(1, threads / size_t(n_gpus))) - 1);
+        // host copies are split over `--threads / gpus` threads (at most 8), like the reference's workers: one half
+        // stages input (this thread + helpers), the other half drains output (the drainer thread + helpers), so that
+        // the two directions run side by side
+        const size_t host_threads = std::min<size_t>(8, std::max<size_t>(2, threads / size_t(n_gpus)));
+        HostPool io_in((host_threads + 1) / 2 - 1), io_out(std::max<size_t>(1, host_threads / 2) - 1);
         constexpr size_t kPiece = size_t(2) << 20;
-        auto par_memcpy = [&](uint8_t *dst, const uint8_t *src_p, size_t len) {
+        auto par_copy = [&](HostPool &io, uint8_t *dst, const uint8_t *src_p, size_t len) {
             const size_t parts = std::min(io.width(), (len + kPiece - 1) / kPiece);
             if (parts <= 1) { std::memcpy(dst, src_p, len); return; }
             const size_t per = ((len + parts - 1) / parts + 4095) & ~size_t(4095);
@@ -793,6 +889,7 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
                 if (lo < len) std::memcpy(dst + lo, src_p + lo, std::min(per, len - lo));
             });
         };
+        auto par_memcpy = [&](uint8_t *dst, const uint8_t *src_p, size_t len) { par_copy(io_out, dst, src_p, len); };
         auto put = [&](const uint8_t *buf, size_t len, uint64_t off) -> int {
             if (of.map) {  // mapped output: plain stores, split over the helper threads, into pages that exist
                 if (off + len > of.map_len) return fail(BLT_ERR_CAPACITY, "output exceeds its upper bound");
@@ -837,61 +934,107 @@ extern "C" int blt_run_tokenizer(const blt_core_config *cfg) {
             pipe = ctx->acquire();
             rc = pipe->ensure(std::min(chunk, n), std::min(kSlots, std::max<size_t>(src.count, 1)), true);
             slog.mark("pipe buffers allocated", sh.device);
-            // Output is delivered one chunk late so chunk k's D2H overlaps chunk k+1's host-side input staging.
-            struct Pending { Slot *sl = nullptr; size_t len = 0, id = 0; } pend;
-            auto flush = [&](Pending &p) -> int {
-                if (!p.sl) return BLT_OK;
-                auto t0 = now();
-                CUDA_TRY(cudaEventSynchronize(p.sl->ev_d2h));
-                // Basic is fixed-ratio: the offset is known up front; otherwise ask the board
-                const int64_t base = (mode == Mode::Basic) ? int64_t(2 * p.id * chunk) : board.base_of(p.id);
-                if (base < 0) return fail(BLT_ERR_IO, "another GPU pipeline failed");
-                t_wait += since(t0);
-                t0 = now();
-                const int w = put(p.sl->h_out, p.len, prefix + uint64_t(base));
-                t_out += since(t0);
-                produced += p.len;
-                p.sl = nullptr;
-                return w;
-            };
+            // Output is drained by a second thread: it waits for chunk k's D2H, asks the board for the chunk's offset
+            // and copies pinned -> output mapping while this thread stages the input of the chunks behind it.
+            struct DrainItem { Slot *sl; size_t len, id; };
+            std::mutex dmu;
+            std::condition_variable dcv;
+            std::deque<DrainItem> dq;
+            bool dstop = false;
+            int drc = BLT_OK;
+            std::string derr;
+            std::vector<size_t> slot_submitted(kSlots, 0), slot_drained(kSlots, 0);
+            std::thread drainer([&] {
+                cudaSetDevice(sh.device);
+                for (;;) {
+                    DrainItem it;
+                    {
+                        std::unique_lock<std::mutex> lk(dmu);
+                        dcv.wait(lk, [&] { return dstop || !dq.empty(); });
+                        if (dq.empty()) return;
+                        it = dq.front();
+                        dq.pop_front();
+                    }
+                    int w = BLT_OK;
+                    if (drc == BLT_OK) {
+                        auto t0 = now();
+                        if (cudaEventSynchronize(it.sl->ev_d2h) != cudaSuccess) w = fail(BLT_ERR_CUDA, "cudaEventSynchronize failed");
+                        // Basic is fixed-ratio: the offset is known up front; otherwise ask the board
+                        const int64_t base = (w != BLT_OK) ? -1 : (mode == Mode::Basic) ? int64_t(2 * it.id * chunk) : board.base_of(it.id);
+                        if (w == BLT_OK && base < 0) w = fail(BLT_ERR_IO, "another GPU pipeline failed");
+                        t_wait += since(t0);
+                        if (w == BLT_OK) {
+                            t0 = now();
+                            w = put(it.sl->h_out, it.len, prefix + uint64_t(base));
+                            t_out += since(t0);
+                            produced += it.len;
+                        }
+                    }
+                    {
+                        std::lock_guard<std::mutex> lk(dmu);
+                        if (w != BLT_OK && drc == BLT_OK) { drc = w; derr = blt_last_error(); board.fail_all(); }
+                        ++slot_drained[size_t(it.sl - pipe->slots.data())];
+                    }
+                    dcv.notify_all();
+                }
+            });
             if (rc == BLT_OK && src.count) {
                 rc = run_slots(
                     st, *pipe, src,
                     [&](size_t id, Slot &sl) {
                         const auto t0 = now();
-                        par_memcpy(sl.h_in, map + id * chunk, src.len_of(id));  // page cache -> pinned
+                        par_copy(io_in, sl.h_in, map + id * chunk, src.len_of(id));  // page cache -> pinned
                         t_in += since(t0);
                         return static_cast<const uint8_t *>(sl.h_in);
                     },
                     [&](size_t id, Slot &sl, size_t len) -> int {
                         board.publish(id, len);  // the length is known before the bytes are back
-                        int w = flush(pend);     // previous chunk: its copy has had a full stage to finish
-                        if (w) return w;
+                        const size_t si = size_t(&sl - pipe->slots.data());
+                        {   // the slot's pinned output buffer is free once its previous chunk has been drained
+                            std::unique_lock<std::mutex> lk(dmu);
+                            dcv.wait(lk, [&] { return drc != BLT_OK || slot_drained[si] == slot_submitted[si]; });
+                            if (drc != BLT_OK) return fail(drc, derr);
+                        }
                         CUDA_TRY(cudaMemcpyAsync(sl.h_out, sl.d_out, len, cudaMemcpyDeviceToHost, pipe->s_d2h));
                         CUDA_TRY(cudaEventRecord(sl.ev_d2h, pipe->s_d2h));
-                        pend.sl = &sl;
-                        pend.len = len;
-                        pend.id = id;
+                        {
+                            std::lock_guard<std::mutex> lk(dmu);
+                            ++slot_submitted[si];
+                            dq.push_back(DrainItem{&sl, len, id});
+                        }
+                        dcv.notify_all();
                         return BLT_OK;
                     });
-                if (rc == BLT_OK) rc = flush(pend);
             }
+            {
+                std::lock_guard<std::mutex> lk(dmu);
+                dstop = true;
+            }
+            dcv.notify_all();
+            drainer.join();
+            if (rc == BLT_OK && drc != BLT_OK) rc = fail(drc, derr);
         }
         sh.total = produced;
         if (rc != BLT_OK) { sh.rc = rc; sh.err = blt_last_error(); board.fail_all(); }
         slog.mark("pipeline drained", sh.device);
         if (slog.on)
-            std::fprintf(stderr, "[blt] gpu%d host seconds: copy-in %.3f, copy-out %.3f, waiting for the device %.3f (%zu threads)\n",
-                         sh.device, t_in, t_out, t_wait, io.width());
+            std::fprintf(stderr, "[blt] gpu%d host seconds: copy-in %.3f, copy-out %.3f, drainer waiting for the device / the offset %.3f (%zu + %zu threads)\n",
+                         sh.device, t_in, t_out, t_wait, io_in.width(), io_out.width());
         {   // from here on this thread only gives device resources back; the files are the main thread's
             std::lock_guard<std::mutex> lk(drain_mu);
             ++drained;
         }
         drain_cv.notify_all();
-        if (pipe) { pipe->release(); }
+        if (pipe) {
+            if (rc != BLT_OK) {  // drain whatever is in flight before the pipe is reused
+                cudaStreamSynchronize(pipe->s_h2d);
+                cudaStreamSynchronize(pipe->s_comp);
+                cudaStreamSynchronize(pipe->s_d2h);
+            }
+            ctx->give_back(std::move(pipe));
+        }
         if (st) blt_strategy_destroy(st);
-        if (ctx) blt_ctx_destroy(ctx);
-        slog.mark("device resources released", sh.device);
+        slog.mark("device resources returned to the pool", sh.device);
     };
 
     std::vector<std::thread> pool;

@@ -69,6 +69,7 @@ struct Pipe {
     std::vector<Slot> slots;
     size_t cap = 0;        // input bytes per slot (device buffers)
     size_t pin_cap = 0;    // input bytes per slot of the pinned staging (0: none)
+    std::vector<cudaEvent_t> piece_ev;  // single-unit calls: one event per output piece (see run_one_unit_pieced)
     Workspace ws;
     int ensure(size_t chunk_cap, size_t n_slots, bool want_pinned);  // want_pinned: staging for chunk_cap bytes too
     void release();
@@ -97,7 +98,7 @@ struct blt_strategy {
     bltk::HashSlot *d_slots = nullptr;    // K3 hash table
     uint32_t *d_can_left = nullptr, *d_can_right = nullptr;
     uint32_t hash_mask = 0;
-    int variant = 0;                      // K2 tile configuration of the exact sweep
+    int variant = 3;                      // K2 exact sweep: 3 = fused single pass (default), 0/1/2 = count/scan/emit forms, 4 = fused 23x2
     bool try_dense = true;                // K2: run the speculative dense pass first
     // Predictor of the speculation.  A failed attempt costs the attempt plus a device-side launch of the
     // exact sweep (~0.1 ms), so after a failure the next `backoff` calls go to the exact sweep directly
