@@ -273,7 +273,33 @@ def chunk_api_leg(np, strat, data, chunk, want, threads_list=(1, 8)):
             "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(want.size) if want is not None else None}
 
 
-def file_leg(np, nat, synth, name, data, left, right, n_gpus, pcie, want=None, reps=3):
+def fresh_page_rate(d, n=1 << 30):
+    """How fast this box produces fresh, mapped pages of a new file in `d` (fallocate + MADV_POPULATE_WRITE from one
+    thread, what the file pipeline's background thread does): the ceiling of any mapped fresh output file here."""
+    import ctypes, mmap
+    libc = ctypes.CDLL(None, use_errno=True)
+    path = os.path.join(d, f"blt_bench_pages_{os.getpid()}")
+    fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        os.ftruncate(fd, n)
+        m = mmap.mmap(fd, n)
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(m))
+        t0 = time.perf_counter()
+        os.posix_fallocate(fd, 0, n)
+        libc.madvise(ctypes.c_void_p(addr), ctypes.c_size_t(n), 23)   # MADV_POPULATE_WRITE
+        dt = time.perf_counter() - t0
+        del addr
+        try:
+            m.close()
+        except BufferError:
+            pass
+        return round(n / dt / 1e9, 2)
+    finally:
+        os.close(fd)
+        os.unlink(path)
+
+
+def file_leg(np, nat, synth, name, data, left, right, n_gpus, pcie, want=None, reps=3, page_gbps=None):
     """blt_run_tokenizer tmpfs -> tmpfs on n_gpus GPUs of this process; wall = the whole call (config, mmap, contexts
     on first use, pipeline, trim).  frac_of_pcie_roofline = max(N_in / BW_h2d, out / BW_d2h) / pipeline time."""
     d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
@@ -300,7 +326,9 @@ def file_leg(np, nat, synth, name, data, left, right, n_gpus, pcie, want=None, r
         t_roof = max(data.size / (bw_in * 1e9), out_bytes / (bw_out * 1e9))
         return {"workload": name, "gpus": n_gpus, "bytes_in": int(data.size), "bytes_out": int(out_bytes),
                 "wall_s_first_call": round(walls[0], 3), "wall_s_best": round(best, 3), "input_GBps": round(data.size / best / 1e9, 2),
-                "pcie_roofline_s": round(t_roof, 4), "frac_of_pcie_roofline": round(t_roof / best, 3), "filesystem": d}
+                "pcie_roofline_s": round(t_roof, 4), "frac_of_pcie_roofline": round(t_roof / best, 3), "filesystem": d,
+                "fresh_output_page_GBps": page_gbps,
+                "frac_of_output_page_ceiling": None if not page_gbps else round(out_bytes / (page_gbps * 1e9) / best, 3)}
     finally:
         for f in (inp, outp, mp):
             if os.path.exists(f):
@@ -522,9 +550,14 @@ def run_ours(args):
         del d_in, d_out, d_ends
         torch.cuda.empty_cache()
         file_to_file = []
+        try:
+            page_gbps = fresh_page_rate("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+        except Exception as e:  # informational only
+            log(f"fresh page probe failed: {e}")
+            page_gbps = None
         tdata, tleft, tright = build_workload(n, 0, args.merges, out=h_in.numpy())      # the headline workload again
         file_to_file.append(file_leg(np, nat, synth, "configs2_text_32768_merges", tdata, tleft, tright, world, pcie,
-                                     want=None if args.no_check else h_out[:out_bytes].numpy()))
+                                     want=None if args.no_check else h_out[:out_bytes].numpy(), page_gbps=page_gbps))
         try:
             import psutil
             free = psutil.virtual_memory().available
@@ -537,7 +570,7 @@ def run_ours(args):
             d5 = synth.text(n5, synth.SEED_CONFIG[5])
             l5, r5 = synth.merges_from_sample(d5, 60000)
             log(f"[rank 0] generated config 5 (8 GiB) in {time.perf_counter() - t0:.1f}s")
-            file_to_file.append(file_leg(np, nat, synth, "configs4_8GiB_60000_merges", d5, l5, r5, world, pcie, reps=2))
+            file_to_file.append(file_leg(np, nat, synth, "configs4_8GiB_60000_merges", d5, l5, r5, world, pcie, reps=2, page_gbps=page_gbps))
             del d5
         else:
             file_to_file.append({"workload": "configs4_8GiB_60000_merges", "skipped": f"needs {5 * n5 >> 30} GiB of free RAM and tmpfs "

@@ -311,6 +311,7 @@ namespace bltc {
 static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **out) {
     auto s = std::unique_ptr<blt_strategy>(new blt_strategy());
     s->ctx = ctx;
+    ctx->retain();
     s->rules = std::move(rules);
     CUDA_TRY(cudaSetDevice(ctx->device));
     bool pairs_ok = true;
@@ -368,6 +369,7 @@ blt_strategy::~blt_strategy() {
     if (d_can_right) cudaFree(d_can_right);
     if (d_detok) cudaFree(d_detok);
     resident.release();
+    if (ctx) ctx->release_ref();
 }
 
 #ifdef BLT_FUSED_PROF
@@ -415,14 +417,19 @@ int blt_ctx_create(int device, blt_ctx **out) {
 void blt_ctx_destroy(blt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (auto &p : ctx->idle) p->release();
-    delete ctx;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (auto &p : ctx->idle) p->release();
+        ctx->idle.clear();
+    }
+    ctx->release_ref();
 }
 
 int blt_strategy_basic(blt_ctx *ctx, blt_strategy **out) {
     if (!ctx || !out) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
     auto s = new blt_strategy();
     s->ctx = ctx;
+    ctx->retain();
     s->mode = Mode::Basic;
     *out = s;
     return BLT_OK;
@@ -432,6 +439,7 @@ int blt_strategy_passthrough(blt_ctx *ctx, blt_strategy **out) {
     if (!ctx || !out) return fail(BLT_ERR_INVALID_INPUT, "NULL argument");
     auto s = new blt_strategy();
     s->ctx = ctx;
+    ctx->retain();
     s->mode = Mode::Passthrough;
     *out = s;
     return BLT_OK;

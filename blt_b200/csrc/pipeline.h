@@ -84,6 +84,11 @@ int detokenize_host(blt_strategy *s, const uint8_t *in, size_t n_bytes, uint8_t 
 struct blt_ctx {
     int device = 0;
     int sm_count = 0;
+    // 1 for the handle the caller holds + 1 per live strategy: blt_ctx_destroy with strategies still alive only gives
+    // the pooled pipes back; the object goes away with the last strategy (a strategy dereferences its context)
+    std::atomic<int> refs{1};
+    void retain() { refs.fetch_add(1, std::memory_order_relaxed); }
+    void release_ref() { if (refs.fetch_sub(1, std::memory_order_acq_rel) == 1) delete this; }
     std::mutex mu;
     std::vector<std::unique_ptr<bltc::Pipe>> idle;  // pipes not currently lent to a call
     std::unique_ptr<bltc::Pipe> acquire();

@@ -328,6 +328,17 @@ def test_basic_output_aligned_to_16_not_32(ctx, torch_mod, oracle):
         assert np.all(h[:off] == 0xA5) and np.all(h[off + 2 * n:] == 0xA5)
 
 
+def test_strategy_outlives_its_context_handle(nat, oracle):
+    """Context.close() before Strategy.close(): the strategy keeps the context alive (reference count) and still works."""
+    c = nat.Context(0)
+    pairs = {(97, 98): 256, (98, 99): 257}
+    s = c.bpe_from_pairs(pairs)
+    c.close()
+    data = np.frombuffer(b"abcabcab" * 1000, dtype=np.uint8)
+    assert np.array_equal(s.tokenize_host(data, chunk_size=4096), oracle.run_buffer("bpe", data, 4096, 2, oracle.Merges(pairs)))
+    s.close()
+
+
 def test_empty_and_capacity_errors(ctx, nat, torch_mod):
     s = ctx.bpe_from_pairs({(97, 98): 256})
     assert s.process_chunk(b"").size == 0                      # tokenizer.rs:57-59
