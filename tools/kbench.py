@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Kernel micro-benchmark: device-resident timings (CUDA events) of K1 (widen) and of every K2 tile
 configuration on the BASELINE.json workloads.  Prints one JSON line per measurement.
-    python tools/kbench.py [--bytes N] [--iters K] [--variants 0,1,2] [--configs 1,2,3,4]"""
+    python tools/kbench.py [--bytes N] [--iters K] [--variants 0,1,2,3,4] [--configs 1,2,3,4,6,7,8,9]
+(6 general map, 7 detokenizer, 8 pair histogram, 9 mixed corpus with 32 768 rules)"""
 import argparse
 import json
 import os
@@ -127,7 +128,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bytes", type=int, default=1 << 30)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--variants", default="0")
+    ap.add_argument("--variants", default="3")
     ap.add_argument("--configs", default="1,2,3,4")
     args = ap.parse_args()
     n, chunk = args.bytes, 16 << 20
@@ -151,6 +152,8 @@ def main():
             data = synth.random_bytes(n, synth.SEED_CONFIG[1])
         elif cfg == 4:
             data = synth.adversarial(n, synth.SEED_CONFIG[4])
+        elif cfg == 9:   # mixed corpus: every byte pair occurs, the 32 768-rule table is a strict subset (the exact sweep's real workload)
+            data = synth.mixed(n, synth.SEED_MIXED)
         else:
             data = synth.text(n, synth.SEED_CONFIG[cfg])
         d_in = torch.from_numpy(data).cuda()
