@@ -11,22 +11,24 @@
 //   count   every worker owns R*512 consecutive bytes of the tile (R rounds of 32 lanes x 16 bytes): both parities
 //           are looked up, the tokens STAY IN REGISTERS, run parity is resolved inside the warp with two ballots
 //           per round under the hypothesis "the warp's carry_in is 0" and the warp's slice is reduced to one carry
-//           function (identity / constant, tokens for carry_in 0, the 0/1-token delta for carry_in 1);
-//   chain   while the workers emit tile i-1 and count tile i+1, the chain warp composes the WG warp functions of
-//           tile i, publishes the tile's function (status A) in the tile's 64-bit descriptor and polls the 192
-//           descriptors in front of it until it sees an inclusive prefix (status P) with nothing missing behind it.
-//           The carry entering every tile of the window comes from ballots (nearest non-identity tile in front of
-//           it), its exact token count is cnt0 - (delta & carry_in), and one warp-wide add gives the offset.  The
-//           window spans more than one round of the deal, so nothing propagates hop by hop inside a round: a tile
-//           is resolved one poll after the tiles dealt with it have published.  The look-back has a whole tile
-//           period of slack before anybody needs its result;
+//           function (identity / constant, tokens for carry_in 0, the 0/1-token delta for carry_in 1).  The last
+//           worker to finish composes the WG functions and publishes the tile's function (status A) in the tile's
+//           64-bit descriptor.  (Looking all R rounds up first and doing the ballot algebra afterwards was measured:
+//           no gain, 1.32 against 1.30 ms per GiB on config 2.)
+//   chain   while the workers emit tile i-1 and count tile i+1, the chain warp polls the 192 descriptors in front of
+//           tile i until it sees an inclusive prefix (status P) with nothing missing behind it.  The carry entering
+//           every tile of the window comes from ballots (nearest non-identity tile in front of it), its exact token
+//           count is cnt0 - (delta & carry_in), and one warp-wide add gives the offset.  The window spans more than
+//           one round of the deal, so nothing propagates hop by hop inside a round;
 //   emit    (one tile behind) every worker compacts the retained tokens of its whole slice into a warp-private
-//           staging line (XOR-swizzled so that the 32 lanes' 2-byte stores spread over the banks; the R rounds are
-//           R independent store chains) and streams whole 4-byte words out.  Only the lanes in front of the
-//           slice's first non-identity segment depend on the carry_in; they are redone when it is 1.
+//           staging line with unpredicated 2-byte stores (a silent position's token is overwritten by the lane's next
+//           emitting one; the R rounds are R independent store chains) and streams whole 16-byte vectors out.  Only
+//           the lanes in front of the slice's first non-identity segment depend on the carry_in; they are redone when
+//           it is 1.  A slice that emits exactly one parity everywhere goes out straight from the registers.
 //
 // Forward progress: a tile only ever waits for tiles with smaller numbers, which belong to resident CTAs that reach
 // them before any larger one, and nothing that publishes a tile's function waits for anything.
+// Measurements, the per-round budget and the variants that were tried: DESIGN.md section 4.
 // Included by kernels.cu inside its anonymous namespace, after sweep3.cuh (ScanFn, scan_compose, start_bits).
 #pragma once
 
