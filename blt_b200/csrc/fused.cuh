@@ -833,6 +833,16 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
     })
 }
 
+// One per device: the event behind the most recent fused launch (see FusedLaunch::launch).
+struct FusedChain {
+    std::mutex mu;
+    cudaEvent_t ev = nullptr;
+};
+inline FusedChain &fused_chain(int dev) {
+    static FusedChain chains[kMaxDevices];
+    return chains[dev];
+}
+
 template <int WG, int R, int D>
 struct FusedLaunch {
     using C = FusedCfg<WG, R, D>;
@@ -867,8 +877,25 @@ struct FusedLaunch {
         size_t grid = tiles;
         if (grid > size_t(sm_count(dev))) grid = size_t(sm_count(dev));
         const size_t chunk = (a.chunk == 0 || a.chunk > a.n) ? a.n : a.chunk;
+        // The look-back makes CTAs wait for tiles of OTHER CTAs of the same launch, which is only safe while all of a
+        // launch's CTAs are resident (grid <= SM count, one CTA per SM).  Two fused launches on different streams could
+        // each get a part of the SMs and wait for their own unscheduled CTAs forever, so fused launches of one device
+        // are chained: each waits (on the device, through an event) for the one enqueued before it, whatever its stream.
+        // Any other kernel may run beside a fused launch: it ends without waiting for anybody and frees its SMs.
+        FusedChain &fc = fused_chain(dev);
+        std::lock_guard<std::mutex> lk(fc.mu);
+        static const bool no_chain = getenv("BLT_FZ_NO_CHAIN") != nullptr;  // test knob: shows the hazard the chain removes
+        if (fc.ev == nullptr) {
+            err = cudaEventCreateWithFlags(&fc.ev, cudaEventDisableTiming);
+            if (err != cudaSuccess) return err;
+        } else if (!no_chain) {
+            err = cudaStreamWaitEvent(stream, fc.ev, 0);
+            if (err != cudaSuccess) return err;
+        }
         fused_sweep_kernel<WG, R, D><<<dim3(unsigned(grid)), dim3(C::THREADS), C::SMEM, stream>>>(
             a, d_table, reinterpret_cast<unsigned long long *>(a.scratch.meta), uint32_t(tiles), (unsigned long long)chunk);
-        return cudaGetLastError();
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        return cudaEventRecord(fc.ev, stream);
     }
 };

@@ -382,6 +382,40 @@ def test_concurrent_process_chunk_on_one_strategy(ctx, oracle):
 
 # ---- the five BASELINE.json configs ----------------------------------------------------------------------
 
+def test_concurrent_fused_launches(nat, oracle, monkeypatch):
+    """Eight host threads, each with its own pipe and stream, push 8 MiB chunks (274 tiles: a full grid of 148 CTAs)
+    through the fused sweep at once.  Two fused launches sharing the SMs could wait for each other's unscheduled CTAs
+    (the look-back needs every CTA of a launch resident); the launches of a device are chained on an event instead."""
+    import threading
+    from blt_b200 import synth
+    monkeypatch.setenv("BLT_DENSE", "0")
+    monkeypatch.setenv("BLT_SWEEP_VARIANT", "3")
+    c = nat.Context(0)
+    n_threads, chunk = 8, 8 * MiB
+    data = synth.mixed(n_threads * chunk, 4242)
+    l, r = synth.merges_from_sample(data, 4096)
+    pairs = {(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))}
+    s = c.bpe_from_pairs(pairs)
+    om = oracle.Merges(pairs)
+    want = [np.frombuffer(oracle.process_chunk("bpe", data[k * chunk:(k + 1) * chunk], om), dtype=np.uint8) for k in range(n_threads)]
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(6):
+                if not np.array_equal(s.process_chunk(data[k * chunk:(k + 1) * chunk]), want[k]):
+                    errs.append(("mismatch", k))
+        except Exception as e:  # pragma: no cover
+            errs.append((repr(e), k))
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(n_threads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    s.close()
+    c.close()
+
+
 def _check_chunks(torch, oracle, om, data, d_out_np, ends, chunk, which, mode="bpe"):
     for k in which:
         lo = 0 if k == 0 else int(ends[k - 1])
