@@ -75,6 +75,8 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
     res->len = 0;
     res->sweeps = 0;
     res->owner = nullptr;
+    res->ratio_to = nullptr;
+    res->n_in = 0;
     res->len_scale = 2;
     if (n == 0) return BLT_OK;
     if (chunk == 0 || chunk > n) chunk = n;
@@ -106,7 +108,14 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
             a.out_cap_tokens = out_cap / 2; a.out_base_tokens = 0;
             a.chunk_ends = d_chunk_ends; a.chunk_ends_base = 0;
             a.scratch = ws.scratch;
-            CUDA_TRY(bltk::launch_bpe_sweep_pairs(a, s->d_table, s->variant, s->want_dense(), stream, &res->launches));
+            int variant = s->variant;
+            if (!s->variant_forced) {
+                const uint32_t r = s->last_ratio_milli.load(std::memory_order_relaxed);
+                if (r != 0 && r < 515) variant = 0;
+            }
+            res->ratio_to = s;
+            res->n_in = n;
+            CUDA_TRY(bltk::launch_bpe_sweep_pairs(a, s->d_table, variant, s->want_dense(), stream, &res->launches));
             res->owner = (res->launches == bltk::kLaunchesDenseAttempt) ? s : nullptr;
             res->kind = DeviceResult::IN_SCRATCH;
             res->sweeps = 1;  // byte keys, ids >= 256: the reference's 2nd sweep cannot merge
@@ -194,6 +203,10 @@ int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res) {
     if (res->len_scale == 1 && reinterpret_cast<const uint32_t *>(h_ctrl)[6] != 0u)
         return fail(BLT_ERR_INVALID_DATA, "token stream contains a token that is not in the table");
     res->len = size_t(h_ctrl[0]) * res->len_scale;
+    if (res->ratio_to && res->n_in) {
+        res->ratio_to->last_ratio_milli.store(uint32_t(std::max<uint64_t>(1, h_ctrl[0] * 1000 / res->n_in)), std::memory_order_relaxed);
+        res->ratio_to = nullptr;
+    }
     res->kind = DeviceResult::KNOWN;
     return BLT_OK;
 }
@@ -205,6 +218,8 @@ int run_detok(blt_strategy *s, Workspace &ws, const uint8_t *d_tokens, size_t n_
     res->len = 0;
     res->sweeps = 0;
     res->owner = nullptr;
+    res->ratio_to = nullptr;
+    res->n_in = 0;
     res->len_scale = 1;
     res->launches = 0;
     if (n_bytes & 1) return fail(BLT_ERR_INVALID_DATA, "token stream has an odd number of bytes");
@@ -350,7 +365,7 @@ static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **ou
         CUDA_TRY(cudaMemcpy(s->d_can_right, cr.data(), 8192, cudaMemcpyHostToDevice));
     }
     // tuning / test switches: tile size of the exact sweep, and whether the dense pass runs in front of it
-    if (const char *v = getenv("BLT_SWEEP_VARIANT")) s->variant = atoi(v);
+    if (const char *v = getenv("BLT_SWEEP_VARIANT")) { s->variant = atoi(v); s->variant_forced = true; }
     if (const char *v = getenv("BLT_DENSE")) {  // 0 = never, always = on every call, else the predictor decides
         s->dense_always = std::string(v) == "always";
         s->try_dense = s->dense_always || atoi(v) != 0;

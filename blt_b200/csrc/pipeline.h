@@ -39,6 +39,8 @@ struct DeviceResult {
     uint32_t sweeps = 0;  // productive + verifying sweeps actually launched
     int launches = 0;     // kernels enqueued by the host
     blt_strategy *owner = nullptr;  // set when the dense pass was attempted: decode_ctrl reports back to it
+    blt_strategy *ratio_to = nullptr;  // byte-pair sweeps: decode_ctrl files tokens-per-byte of this call there
+    size_t n_in = 0;                   //   (input elements of the call)
     uint32_t len_scale = 2;         // bytes per unit of the device's total (2: tokens, 1: detokenizer bytes)
     int rc = 0;                     // a result settled on its caller's behalf: the code and message it ended with
     std::string err;
@@ -110,6 +112,11 @@ struct blt_strategy {
     // (16, doubling to 1024 while the probes keep failing); one success makes every call dense again.
     std::atomic<uint32_t> dense_skip{0}, dense_backoff{0};
     bool dense_always = false;            // BLT_DENSE=always: attempt on every call (tests)
+    // Which exact sweep a byte-pair call takes when BLT_SWEEP_VARIANT does not say: the fused single pass, except that
+    // input on which (nearly) every pair merges (the last call emitted < 0.515 tokens per byte) goes to the three-launch
+    // form, which is faster there (0.91 against 1.00 ms per GiB: 32 warps per SM, no look-back) and slower elsewhere.
+    bool variant_forced = false;
+    std::atomic<uint32_t> last_ratio_milli{0};  // 1000 * tokens / input bytes of the most recent call, 0: none yet
     bool want_dense();
     void dense_feedback(bool failed);
     std::mutex detok_mu;                  // detokenizer table, built on first use

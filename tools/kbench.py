@@ -128,7 +128,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bytes", type=int, default=1 << 30)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--variants", default="3")
+    ap.add_argument("--variants", default="auto")
     ap.add_argument("--configs", default="1,2,3,4")
     args = ap.parse_args()
     n, chunk = args.bytes, 16 << 20
@@ -157,20 +157,22 @@ def main():
         else:
             data = synth.text(n, synth.SEED_CONFIG[cfg])
         d_in = torch.from_numpy(data).cuda()
-        variants = [None] if cfg == 1 else [int(v) for v in args.variants.split(",")]
+        variants = [None] if cfg == 1 else [(-1 if v == "auto" else int(v)) for v in args.variants.split(",")]
         for v in variants:
-            if v is not None:
+            if v is not None and v >= 0:
                 os.environ["BLT_SWEEP_VARIANT"] = str(v)
+            else:
+                os.environ.pop("BLT_SWEEP_VARIANT", None)   # the library chooses (fused, or three launches on all-merging input)
             ctx = nat.Context(0)
             if cfg == 1:
                 strat, name = ctx.basic(), "widen"
             elif cfg == 4:
                 strat = ctx.bpe_from_pairs({p_: 256 + i for i, p_ in enumerate(synth.adversarial_pairs())})
-                name = VARIANT_NAMES[v]
+                name = VARIANT_NAMES[v] if v >= 0 else "auto"
             else:
                 l, r = synth.merges_from_sample(data, 256 if cfg == 2 else 32768)
                 strat = ctx.bpe_from_pairs({(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))})
-                name = VARIANT_NAMES[v]
+                name = VARIANT_NAMES[v] if v >= 0 else "auto"
             if cfg != 1:
                 name = ("dense+" if os.environ.get("BLT_DENSE", "1") != "0" else "") + name
             out_len, med, best = time_resident(strat, d_in, n, chunk, d_out, args.iters)
