@@ -57,7 +57,34 @@ int Workspace::ensure_work(size_t chunk_bytes) {
     work_chunk = chunk_bytes;
     return BLT_OK;
 }
+void Workspace::release_lanes() {
+    for (GenLane &l : lanes) {
+        if (l.d_scratch) cudaFree(l.d_scratch);
+        for (auto &p : l.d_work) if (p) cudaFree(p);
+        if (l.d_align) cudaFree(l.d_align);
+        if (l.h_ctrl) cudaFreeHost(l.h_ctrl);
+    }
+    lanes.clear();
+    lane_chunk = 0;
+}
+int Workspace::ensure_lanes(size_t chunk_bytes, size_t n_lanes) {
+    if (chunk_bytes > lane_chunk) release_lanes();
+    lane_chunk = std::max(lane_chunk, chunk_bytes);
+    while (lanes.size() < n_lanes) {
+        lanes.emplace_back();
+        GenLane &l = lanes.back();
+        const size_t elems = std::max<size_t>(lane_chunk, 1u << 20);
+        CUDA_TRY(cudaMalloc(&l.d_scratch, bltk::sweep_scratch_bytes(elems)));
+        l.scratch = bltk::sweep_scratch_carve(l.d_scratch, elems);
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&l.d_work[0]), 2 * lane_chunk + 64));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&l.d_work[1]), 2 * lane_chunk + 64));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&l.d_align), lane_chunk + 64));
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&l.h_ctrl), 64, cudaHostAllocDefault));
+    }
+    return BLT_OK;
+}
 void Workspace::release() {
+    release_lanes();
     if (d_scratch) cudaFree(d_scratch);
     for (auto &p : d_work) if (p) cudaFree(p);
     if (d_align) cudaFree(d_align);
@@ -122,53 +149,70 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
             return BLT_OK;
         }
         case Mode::BpeGeneral: {
-            int rc = ws.ensure_scratch(chunk);
-            if (rc) return rc;
-            rc = ws.ensure_work(chunk);
-            if (rc) return rc;
+            // The loop of tokenizer.rs:63-86 (sweep until one merges nothing), for up to 8 chunks at a time: every chunk
+            // of the batch launches its next sweep, ONE host synchronisation reads all their "merged anything" flags
+            // and totals, chunks that are done drop out.  (Round 1 synchronised once per sweep and chunk.)
             const bltk::HashTableView view{s->d_slots, s->hash_mask, s->d_can_left, s->d_can_right};
             const size_t n_chunks = (n + chunk - 1) / chunk;
+            size_t batch = std::min<size_t>(n_chunks, 8);
+            while (batch > 1 && batch * 5 * chunk > (size_t(2) << 30)) --batch;  // at most 2 GiB of ping-pong buffers
+            int rc = ws.ensure_lanes(chunk, batch);
+            if (rc) return rc;
             std::vector<uint64_t> ends(n_chunks);
             size_t out_bytes = 0;
             uint32_t max_sweeps = 0;
             res->launches = 0;
-            for (size_t k = 0; k < n_chunks; ++k) {
-                const size_t len = std::min(chunk, n - k * chunk);
-                const uint8_t *src = d_in + k * chunk;
-                if (reinterpret_cast<uintptr_t>(src) & 15u) {  // only when chunk is not a multiple of 16
-                    CUDA_TRY(cudaMemcpyAsync(ws.d_align, src, len, cudaMemcpyDeviceToDevice, stream));
-                    src = ws.d_align;
+            struct Live { const void *cur; size_t n; bool u16, active; int which; uint32_t sweeps; };
+            for (size_t k0 = 0; k0 < n_chunks; k0 += batch) {
+                const size_t nb = std::min(batch, n_chunks - k0);
+                std::vector<Live> live(nb);
+                for (size_t j = 0; j < nb; ++j) {
+                    const size_t len = std::min(chunk, n - (k0 + j) * chunk);
+                    const uint8_t *src = d_in + (k0 + j) * chunk;
+                    if (reinterpret_cast<uintptr_t>(src) & 15u) {  // only when chunk is not a multiple of 16
+                        CUDA_TRY(cudaMemcpyAsync(ws.lanes[j].d_align, src, len, cudaMemcpyDeviceToDevice, stream));
+                        src = ws.lanes[j].d_align;
+                    }
+                    live[j] = Live{src, len, false, true, 0, 0};
                 }
-                const void *cur = src;
-                size_t cur_n = len;
-                bool cur_u16 = false;
-                int which = 0;
-                uint32_t sweeps = 0;
-                for (;;) {  // the loop at tokenizer.rs:63-86, one launch per sweep
-                    bltk::SweepArgs a{};
-                    a.in = cur; a.n = cur_n; a.chunk = 0;
-                    a.out = reinterpret_cast<uint16_t *>(ws.d_work[which]);
-                    a.out_cap_tokens = chunk; a.out_base_tokens = 0;
-                    a.chunk_ends = nullptr; a.chunk_ends_base = 0;
-                    a.scratch = ws.scratch;
-                    CUDA_TRY(bltk::launch_bpe_sweep_hash(a, view, cur_u16, stream));
-                    CUDA_TRY(cudaMemcpyAsync(ws.h_ctrl, ws.scratch.ctrl, 32, cudaMemcpyDeviceToHost, stream));
+                for (bool any = true; any;) {
+                    for (size_t j = 0; j < nb; ++j) {
+                        if (!live[j].active) continue;
+                        Workspace::GenLane &ln = ws.lanes[j];
+                        bltk::SweepArgs a{};
+                        a.in = live[j].cur; a.n = live[j].n; a.chunk = 0;
+                        a.out = reinterpret_cast<uint16_t *>(ln.d_work[live[j].which]);
+                        a.out_cap_tokens = chunk; a.out_base_tokens = 0;
+                        a.chunk_ends = nullptr; a.chunk_ends_base = 0;
+                        a.scratch = ln.scratch;
+                        CUDA_TRY(bltk::launch_bpe_sweep_hash(a, view, live[j].u16, stream));
+                        CUDA_TRY(cudaMemcpyAsync(ln.h_ctrl, ln.scratch.ctrl, 32, cudaMemcpyDeviceToHost, stream));
+                        ++res->launches;
+                    }
                     CUDA_TRY(cudaStreamSynchronize(stream));
-                    ++sweeps;
-                    ++res->launches;
-                    const uint64_t total = ws.h_ctrl[0];
-                    const uint32_t merged = reinterpret_cast<const uint32_t *>(ws.h_ctrl)[3];
-                    cur = ws.d_work[which];
-                    cur_n = size_t(total);
-                    cur_u16 = true;
-                    which ^= 1;
-                    if (!merged) break;  // tokenizer.rs:83-85
+                    any = false;
+                    for (size_t j = 0; j < nb; ++j) {
+                        if (!live[j].active) continue;
+                        Workspace::GenLane &ln = ws.lanes[j];
+                        ++live[j].sweeps;
+                        const uint64_t total = ln.h_ctrl[0];
+                        const uint32_t merged = reinterpret_cast<const uint32_t *>(ln.h_ctrl)[3];
+                        if (reinterpret_cast<const uint32_t *>(ln.h_ctrl)[4]) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+                        live[j].cur = ln.d_work[live[j].which];
+                        live[j].n = size_t(total);
+                        live[j].u16 = true;
+                        live[j].which ^= 1;
+                        if (!merged) live[j].active = false;  // tokenizer.rs:83-85
+                        else any = true;
+                    }
                 }
-                if (out_bytes + 2 * cur_n > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
-                CUDA_TRY(cudaMemcpyAsync(d_out + out_bytes, cur, 2 * cur_n, cudaMemcpyDeviceToDevice, stream));
-                out_bytes += 2 * cur_n;
-                ends[k] = out_bytes;
-                max_sweeps = std::max(max_sweeps, sweeps);
+                for (size_t j = 0; j < nb; ++j) {
+                    if (out_bytes + 2 * live[j].n > out_cap) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
+                    CUDA_TRY(cudaMemcpyAsync(d_out + out_bytes, live[j].cur, 2 * live[j].n, cudaMemcpyDeviceToDevice, stream));
+                    out_bytes += 2 * live[j].n;
+                    ends[k0 + j] = out_bytes;
+                    max_sweeps = std::max(max_sweeps, live[j].sweeps);
+                }
             }
             if (d_chunk_ends) {
                 CUDA_TRY(cudaMemcpyAsync(d_chunk_ends, ends.data(), n_chunks * 8, cudaMemcpyHostToDevice, stream));

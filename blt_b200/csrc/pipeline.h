@@ -28,8 +28,21 @@ struct Workspace {
     uint8_t *d_align = nullptr;               // general path: 16-byte aligned copy of a chunk
     size_t work_chunk = 0;
     uint64_t *h_ctrl = nullptr;               // pinned mirror of the scratch control block
+    // general (multi-sweep) path: several chunks advance together, one host synchronisation per sweep LEVEL of the batch
+    // instead of one per sweep and chunk; every chunk of the batch needs its own scratch, ping-pong buffers and mirror
+    struct GenLane {
+        void *d_scratch = nullptr;
+        bltk::SweepScratch scratch{};
+        uint8_t *d_work[2] = {nullptr, nullptr};
+        uint8_t *d_align = nullptr;
+        uint64_t *h_ctrl = nullptr;
+    };
+    std::vector<GenLane> lanes;
+    size_t lane_chunk = 0;
     int ensure_scratch(size_t n_elems);
     int ensure_work(size_t chunk_bytes);
+    int ensure_lanes(size_t chunk_bytes, size_t n_lanes);
+    void release_lanes();
     void release();
 };
 
