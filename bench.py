@@ -166,7 +166,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->u16", "data": "synthetic",
         "config": workload_config(args),
-        "notes": {"arm": "the same workload on the host cores (restated CPU path, in memory), each step = a bounded prefix of it"},
+        "notes": {"arm": "the same workload on the host cores (restated CPU path, in memory), each step = a bounded prefix of it",
+                  "maps_libblt_cuda": any("libblt_cuda" in ln for ln in open("/proc/self/maps"))},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
                          "sample": f"first {sample >> 20} MiB of the workload per step, in memory, {threads} threads"},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

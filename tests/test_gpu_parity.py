@@ -848,6 +848,29 @@ def test_cli_file_to_file_and_stdin(oracle, tmp_path):
     assert (tmp_path / "o3.bin").read_bytes() == b""
 
 
+def test_output_that_cannot_grow_is_an_io_error(tmp_path):
+    """ADVICE round 1: a full filesystem must surface as an error (the reference returns io::Error and exits 1), never as
+    a SIGBUS from the output mapping.  A file-size limit makes the output's ftruncate / fallocate / pwrite fail with
+    EFBIG: the CLI must exit 1 with a message, and the same run without the limit must succeed."""
+    import resource
+    import signal
+    blt = os.path.join(ROOT, "blt_b200", "lib", "blt")
+    inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    rng = np.random.default_rng(7)
+    rng.integers(0, 256, size=4 * MiB, dtype=np.uint8).tofile(inp)
+
+    def limited():
+        signal.signal(signal.SIGXFSZ, signal.SIG_IGN)
+        resource.setrlimit(resource.RLIMIT_FSIZE, (1 * MiB, 1 * MiB))
+
+    r = subprocess.run([blt, "-i", inp, "-o", outp, "--chunksize", "1MB"], capture_output=True, text=True, preexec_fn=limited, timeout=300)
+    assert r.returncode == 1, (r.returncode, r.stderr[-500:])      # not -SIGBUS, not 0
+    assert r.stderr.strip() != ""
+    r = subprocess.run([blt, "-i", inp, "-o", outp, "--chunksize", "1MB"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert os.path.getsize(outp) == 8 * MiB
+
+
 def test_python_bytetokenizer(oracle, tmp_path):
     """The value-free smoke tests of blt_python/tests/test_tokenizer.py, with the values pinned."""
     import blt_b200

@@ -299,3 +299,26 @@ int main(void) {
                     "-L", libdir, "-lblt_cuda", "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("ok "), (r.returncode, r.stdout, r.stderr)
+
+
+def test_bench_reference_arm_is_clean_and_prints_the_same_config():
+    """bench.py --impl reference: runs on the oracle only (no libblt_cuda.so mapped), prints the contract's keys and
+    the same `config` object the product arm builds (reference-arm hygiene)."""
+    import importlib.util
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--bytes", str(32 << 20), "--merges", "2048"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0
+    assert line["notes"]["maps_libblt_cuda"] is False
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class A:
+        bytes, merges = 32 << 20, 2048
+    assert line["config"] == mod.workload_config(A)
