@@ -229,15 +229,18 @@ __device__ __forceinline__ void fz_warp_copy(const SweepArgs &a, uint32_t t, int
 
 // Where tile t meets chunk walls - chain lane 0.  Chunks are at least a tile long, so a tile holds at most one chunk
 // boundary; the input's last tile may hold the end of the input as well.
+// ck_hint / rem_hint: the chunk the tile starts in and its offset there when the caller tracks them incrementally
+// (rem_hint = ~0: not known, divide).
 template <class C>
 __device__ __forceinline__ void fz_tile_geometry(const SweepArgs &a, unsigned long long chunk, unsigned long long t, uint32_t n_tiles,
-                                                 unsigned long long last_ck, FusedShared *gs, uint32_t slot) {
+                                                 unsigned long long last_ck, FusedShared *gs, uint32_t slot,
+                                                 unsigned long long ck_hint = 0, unsigned long long rem_hint = ~0ull) {
     uint32_t flags = 0, wall0 = FZ_NO_WALL, wall1 = FZ_NO_WALL, len = 0;
     unsigned long long ck = 0;
     if (t < n_tiles) {
         const unsigned long long base = t * C::TILE;
-        ck = base / chunk;
-        const unsigned long long rem = base - ck * chunk;  // the tile's offset in the chunk it starts in
+        ck = (rem_hint != ~0ull) ? ck_hint : base / chunk;
+        const unsigned long long rem = (rem_hint != ~0ull) ? rem_hint : base - ck * chunk;  // the tile's offset in the chunk it starts in
         len = (a.n - base < (unsigned long long)C::TILE) ? uint32_t(a.n - base) : uint32_t(C::TILE);
         if (rem == 0) flags |= FZ_F_START;
         const unsigned long long to_last = chunk - 1 - rem;  // distance to the last element of the chunk the tile starts in
@@ -325,44 +328,44 @@ __device__ __forceinline__ bool fz_chain_poll(const SweepArgs &a, FusedShared *g
         if (idx >= 0) d[j] = ld_desc(desc + idx);
     }
     int qw = -1, qb = 0;  // word and bit of the nearest inclusive prefix
-    bool hole = false;    // a tile nearer than it has published nothing yet
+    // (every branch below is warp-uniform: ballots; a poll that cannot succeed ends after the word with the hole)
 #pragma unroll
     for (int j = 0; j < LB; ++j) {
-        const uint32_t st = uint32_t(d[j] >> 62);
-        const uint32_t pmj = __ballot_sync(FULL, st == 2u);
-        const uint32_t zmj = __ballot_sync(FULL, st == 0u);
         if (qw < 0) {
+            const uint32_t st = uint32_t(d[j] >> 62);
+            const uint32_t pmj = __ballot_sync(FULL, st == 2u);
+            const uint32_t zmj = __ballot_sync(FULL, st == 0u);
             if (pmj != 0u) {
                 qw = j;
                 qb = __ffs(pmj) - 1;
-                if (zmj & ((1u << qb) - 1u)) hole = true;
+                if (zmj & ((1u << qb) - 1u)) {  // a tile nearer than the prefix has published nothing yet
+                    FZ_PROF(if (prof_holes != nullptr) { *prof_holes = __popc(zmj & ((1u << qb) - 1u)); *prof_q = uint32_t(32 * qw + qb); })
+                    return false;
+                }
             } else if (zmj != 0u) {
-                hole = true;
+                FZ_PROF(if (prof_holes != nullptr) { *prof_holes = __popc(zmj); *prof_q = 999u; })
+                return false;
             }
         }
     }
-    FZ_PROF(if (prof_holes != nullptr) {
-        uint32_t nh = 0;  // unpublished tiles in front of the nearest prefix (or in the whole window)
-        for (int j = 0; j < LB; ++j) {
-            const uint32_t zmj = __ballot_sync(FULL, uint32_t(d[j] >> 62) == 0u);
-            if (qw < 0 || j < qw) nh += __popc(zmj);
-            else if (j == qw) nh += __popc(zmj & ((1u << qb) - 1u));
-        }
-        *prof_holes = nh;
-        *prof_q = qw < 0 ? 999u : uint32_t(32 * qw + qb);
-    })
-    if (qw < 0 || hole) return false;
+    if (qw < 0) {
+        FZ_PROF(if (prof_holes != nullptr) { *prof_holes = 0; *prof_q = 999u; })
+        return false;
+    }
+    FZ_PROF(if (prof_holes != nullptr) { *prof_holes = 0; *prof_q = uint32_t(32 * qw + qb); })
     const int q = 32 * qw + qb;
     // The carry leaving position x: P.carry at q, the constant of a non-identity tile, else whatever enters it.
     // nim = "non-identity" (with q itself), cm = that carry.  up_c[j]: the carry of the nearest non-identity position
-    // in words >= j (warp-uniform, filled from the far end).
+    // in words >= j (warp-uniform, filled from the far end).  Words behind the prefix's word take no part.
     uint32_t nim[LB], cm[LB];
 #pragma unroll
     for (int j = 0; j < LB; ++j) {
-        nim[j] = __ballot_sync(FULL, (d[j] & FZ_A_ID) == 0ull);
-        cm[j] = __ballot_sync(FULL, (d[j] & FZ_A_CST) != 0ull);
-        if (j > qw) nim[j] = 0u;
-        if (j == qw) nim[j] = (nim[j] & ((1u << qb) - 1u)) | (1u << qb);
+        nim[j] = 0u; cm[j] = 0u;
+        if (j <= qw) {
+            nim[j] = __ballot_sync(FULL, (d[j] & FZ_A_ID) == 0ull);
+            cm[j] = __ballot_sync(FULL, (d[j] & FZ_A_CST) != 0ull);
+            if (j == qw) nim[j] = (nim[j] & ((1u << qb) - 1u)) | (1u << qb);
+        }
     }
     uint32_t up_c[LB + 1];
     up_c[LB] = 0u;
@@ -374,18 +377,18 @@ __device__ __forceinline__ bool fz_chain_poll(const SweepArgs &a, FusedShared *g
     uint32_t e = 0;
 #pragma unroll
     for (int j = 0; j < LB; ++j) {
-        // the carry entering position 32j + lane leaves the nearest non-identity position behind it
-        const uint32_t above = (lane < 31) ? (nim[j] >> (lane + 1)) : 0u;
-        const uint32_t cin = above ? ((cm[j] >> (lane + __ffs(above))) & 1u) : up_c[j + 1];
-        if (32 * j + lane < q) e += uint32_t(d[j] & 0xffffffffull) - (((d[j] & FZ_A_DELTA) && cin) ? 1u : 0u);
+        if (j <= qw) {
+            // the carry entering position 32j + lane leaves the nearest non-identity position behind it
+            const uint32_t above = (lane < 31) ? (nim[j] >> (lane + 1)) : 0u;
+            const uint32_t cin = above ? ((cm[j] >> (lane + __ffs(above))) & 1u) : up_c[j + 1];
+            if (32 * j + lane < q) e += uint32_t(d[j] & 0xffffffffull) - (((d[j] & FZ_A_DELTA) && cin) ? 1u : 0u);
+        }
     }
     e = __reduce_add_sync(FULL, e);
     unsigned long long pdesc = 0;
 #pragma unroll
-    for (int j = 0; j < LB; ++j) {
-        const unsigned long long v = __shfl_sync(FULL, d[j], qb);
-        if (j == qw) pdesc = v;
-    }
+    for (int j = 0; j < LB; ++j)
+        if (j == qw) pdesc = __shfl_sync(FULL, d[j], qb);
     const unsigned long long base = (pdesc & FZ_COUNT) + e;
     const uint32_t c_in = pd.starts ? 0u : up_c[0];  // the nearest non-identity position's carry enters this tile
     const uint32_t c_out = pd.tf.id ? c_in : pd.tf.cst;
@@ -479,6 +482,28 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         uint32_t n_pend = 0;            // pend[0] is the oldest one
         uint32_t it = 0;                 // the next iteration of this CTA to be counted
         uint32_t idle = 0;
+        // Geometry of the iterations ahead: iteration g_it (the next one to lay out) is tile g_t, which starts g_rem bytes
+        // into chunk g_ck; the static deal advances by gridDim.x tiles per iteration, so no division per tile.
+        uint32_t owed = 0, g_it = uint32_t(D) + 1u;
+        const unsigned long long step_bytes = (unsigned long long)gridDim.x * C::TILE;
+        const unsigned long long step_ck = step_bytes / chunk, step_rem = step_bytes % chunk;
+        unsigned long long g_t = (unsigned long long)blockIdx.x + (unsigned long long)g_it * gridDim.x;
+        unsigned long long g_ck = (g_t * C::TILE) / chunk, g_rem = (g_t * C::TILE) % chunk;
+        auto lay_out = [&]() {
+            while (owed != 0) {  // warp-uniform
+                if (lane == 0) {
+                    if (DYN) fz_tile_geometry<C>(a, chunk, fz_claim<true>(claim, n_tiles, g_it), n_tiles, last_ck, gs, g_it % GS);
+                    else fz_tile_geometry<C>(a, chunk, g_t < n_tiles ? g_t : 0xffffffffull, n_tiles, last_ck, gs, g_it % GS, g_ck, g_rem);
+                }
+                g_t += gridDim.x;
+                g_ck += step_ck;
+                g_rem += step_rem;
+                if (g_rem >= chunk) { g_rem -= chunk; ++g_ck; }
+                ++g_it;
+                --owed;
+            }
+            __syncwarp();
+        };
         FZ_PROF(long long pc_spread = 0; long long pc_pick = 0; long long pc_res = 0; long long pc_polls = 0; long long pc_tiles = 0; long long t_pick[D];
                 long long pc_poll_cyc = 0; long long pc_first_holes = 0; long long pc_first_q = 0; long long pc_first_age = 0; long long pc_firsts = 0;
                 uint32_t pc_last_polled = 0xffffffffu;)
@@ -499,10 +524,9 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 p.cur = nxt; p.par = slot;
                 FZ_PROF({ const long long now = clock64(); pc_spread += gs->t_pub[slot] - gs->t_first[slot]; pc_pick += now - gs->t_pub[slot];
                           for (int d = 0; d < D; ++d) if (uint32_t(d) == n_pend) t_pick[d] = gs->t_pub[slot]; ++pc_tiles; })
-                // claim the tile of iteration it+D+1; its slot was last read 2D iterations ago; the `resolved` arrive below
-                // releases it to the workers
-                if (lane == 0) fz_tile_geometry<C>(a, chunk, fz_claim<DYN>(claim, n_tiles, it + D + 1), n_tiles, last_ck, gs, (it + D + 1) % GS);
-                __syncwarp();
+                // the geometry of iteration it+D+1 is laid out below, behind the poll (owed = iterations picked up whose
+                // geometry is still to be written; the `resolved` arrive of the tile releases it to the workers)
+                ++owed;
 #pragma unroll
                 for (int d = 0; d < D; ++d)
                     if (uint32_t(d) == n_pend) pend[d] = p;
@@ -524,13 +548,15 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
 #endif
                 const uint32_t slot = pend[0].par;
                 FZ_PROF({ pc_res += clock64() - t_pick[0]; for (int d = 0; d + 1 < D; ++d) t_pick[d] = t_pick[d + 1]; })
+                lay_out();  // (only if this tile was picked up in this very turn of the loop)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_resolved + 8 * slot);  // releases res[slot] and the geometry written above
+                if (lane == 0) mbar_arrive(bar_resolved + 8 * slot);  // releases res[slot] and the geometry written so far
 #pragma unroll
                 for (int d = 0; d + 1 < D; ++d) pend[d] = pend[d + 1];
                 --n_pend;
                 progress = true;
             }
+            lay_out();
             if (!progress) {
                 if (++idle == (1u << 24)) {  // seconds: somebody died; fail the launch instead of hanging
                     *a.scratch.overflow = 3u;
