@@ -24,7 +24,11 @@ index = args.only if args.only >= 0 else 0
 while time.time() < t_end:
     rng = random.Random(args.seed * 1000003 + index)
     nrng = np.random.default_rng(args.seed * 1000003 + index)
-    os.environ["BLT_SWEEP_VARIANT"] = str(rng.choice([0, 1, 2, 3, 3, 4, 4]))
+    v = rng.choice([0, 1, 2, 3, 3, 4, 4, None, None])   # None: the library picks the exact form per call
+    if v is None:
+        os.environ.pop("BLT_SWEEP_VARIANT", None)
+    else:
+        os.environ["BLT_SWEEP_VARIANT"] = str(v)
     os.environ["BLT_DENSE"] = rng.choice(["0", "1", "always"])
     ctx = nat.Context(0)
     alpha = rng.choice([2, 3, 5, 26, 256])
@@ -120,7 +124,7 @@ while time.time() < t_end:
     ok = not bad
     if not ok:
         fails += 1
-        print("MISMATCH", index, bad, dict(variant=os.environ["BLT_SWEEP_VARIANT"], dense=os.environ["BLT_DENSE"], n=n, chunk=chunk, alpha=alpha,
+        print("MISMATCH", index, bad, dict(variant=os.environ.get("BLT_SWEEP_VARIANT", "auto"), dense=os.environ["BLT_DENSE"], n=n, chunk=chunk, alpha=alpha,
                                style=style, density=density, rules=len(pairs), gap=gap), flush=True)
     s.close()
     ctx.close()
