@@ -238,7 +238,7 @@ int finish_result(Workspace &ws, cudaStream_t stream, DeviceResult *res) {
 int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res) {
     const uint32_t overflow = reinterpret_cast<const uint32_t *>(h_ctrl)[4];
     if (overflow == 2u) return fail(BLT_ERR_CUDA, "device-side launch of the exact sweep was refused");
-    if (overflow == 3u) return fail(BLT_ERR_CUDA, "the fused sweep timed out waiting for a tile (look-back or bulk copy)");
+    if (overflow == 3u) return fail(BLT_ERR_CUDA, "a single-pass kernel timed out waiting for a tile (look-back or bulk copy)");
     if (overflow) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
     if (res->owner) {  // the dense pass was attempted: tell the predictor how it went
         res->owner->dense_feedback(reinterpret_cast<const uint32_t *>(h_ctrl)[5] != 0u);
@@ -278,7 +278,7 @@ int run_detok(blt_strategy *s, Workspace &ws, const uint8_t *d_tokens, size_t n_
     }
     int rc = s->ensure_detok();
     if (rc) return rc;
-    rc = ws.ensure_scratch(1);
+    rc = ws.ensure_scratch(n_bytes / 2);  // the fused form keeps one 8-byte descriptor per 32 768 tokens in the scratch meta
     if (rc) return rc;
     bltk::DetokArgs a{};
     a.in = reinterpret_cast<const uint16_t *>(d_tokens);
@@ -289,9 +289,10 @@ int run_detok(blt_strategy *s, Workspace &ws, const uint8_t *d_tokens, size_t n_
     a.limit = s->detok_limit;
     a.holes = s->detok_holes;
     a.scratch = ws.scratch;
-    CUDA_TRY(bltk::launch_detokenize(a, stream));
+    int launches = 0;
+    CUDA_TRY(bltk::launch_detokenize(a, s->detok_variant, stream, &launches));
     res->kind = DeviceResult::IN_SCRATCH;
-    res->launches = bltk::kLaunchesDetok;
+    res->launches = launches;
     return BLT_OK;
 }
 
@@ -335,6 +336,8 @@ int blt_strategy::ensure_detok() {
     }
     std::vector<uint16_t> dec(bltk::kPairTableEntries, 0);
     std::vector<uint32_t> exists(2048, 0);
+    for (uint32_t b = 0; b < 256; ++b) dec[b] = uint16_t(b);  // a plain byte decodes to itself: one lookup whatever the width
+    for (uint32_t w = 0; w < 8; ++w) exists[w] = 0xffffffffu;
     // later duplicates of a key overwrite (HashMap::insert, config_loader.rs:39): invert the FINAL map
     std::vector<int32_t> final_id(65536, -1);
     for (const auto &r : rules) final_id[size_t(r.left) | (size_t(r.right) << 8)] = int32_t(r.value);
@@ -410,6 +413,7 @@ static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **ou
     }
     // tuning / test switches: tile size of the exact sweep, and whether the dense pass runs in front of it
     if (const char *v = getenv("BLT_SWEEP_VARIANT")) { s->variant = atoi(v); s->variant_forced = true; }
+    if (const char *v = getenv("BLT_DETOK_VARIANT")) s->detok_variant = atoi(v);
     if (const char *v = getenv("BLT_DENSE")) {  // 0 = never, always = on every call, else the predictor decides
         s->dense_always = std::string(v) == "always";
         s->try_dense = s->dense_always || atoi(v) != 0;

@@ -478,7 +478,9 @@ cudaError_t launch_pair_hist(const unsigned char *d_in, size_t n, unsigned long 
     return launch_pair_hist_impl(d_in, n, d_counts, zero_first, stream);
 }
 
-cudaError_t launch_detokenize(const DetokArgs &a, cudaStream_t stream) { return launch_detok_impl(a, stream); }
+cudaError_t launch_detokenize(const DetokArgs &a, int variant, cudaStream_t stream, int *launches) {
+    return launch_detok_impl(a, variant, stream, launches);
+}
 
 #ifdef BLT_FUSED_PROF
 cudaError_t debug_fused_profile(unsigned long long *host_out, size_t n_words) {

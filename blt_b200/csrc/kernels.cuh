@@ -82,13 +82,14 @@ struct DetokArgs {
     size_t n_tok;
     uint8_t *out;            // device, 16-byte aligned
     size_t out_cap;          // bytes
-    const uint16_t *table;   // device: 65536 x u16 (id -> l | r << 8), then 2048 x u32 "id exists" bitmap
+    const uint16_t *table;   // device: 65536 x u16 (id -> l | r << 8; id < 256 -> id), then 2048 x u32 "id exists" bitmap
     uint32_t limit;          // ids >= limit do not exist
     uint32_t holes;          // 1: ids below limit may be missing too (consult the bitmap)
     SweepScratch scratch;    // total_tokens receives the output BYTES; ctrl word 6 = "unknown token seen"
 };
-cudaError_t launch_detokenize(const DetokArgs &a, cudaStream_t stream);
-constexpr int kLaunchesDetok = 3;
+// variant 0: three launches (count, scan, emit); 1: the fused single pass (needs n_tok / 2048 + 8 bytes of scratch meta,
+// else it falls back to the three launches).  *launches receives the number of kernels launched.
+cudaError_t launch_detokenize(const DetokArgs &a, int variant, cudaStream_t stream, int *launches);
 
 // Adjacent-byte-pair histogram (pairhist.cuh): d_counts[b0 << 8 | b1] += occurrences, 65 536 x u64
 // (zero_first: cleared by the launch; otherwise accumulated into).

@@ -119,6 +119,7 @@ struct blt_strategy {
     uint32_t *d_can_left = nullptr, *d_can_right = nullptr;
     uint32_t hash_mask = 0;
     int variant = 3;                      // K2 exact sweep: 3 = fused single pass (default), 0/1/2 = count/scan/emit forms, 4 = fused 23x2
+    int detok_variant = 0;                // detokenizer: 0 = count/scan/emit (default, measured faster), 1 = fused single pass (BLT_DETOK_VARIANT)
     bool try_dense = true;                // K2: run the speculative dense pass first
     // Predictor of the speculation.  A failed attempt costs the attempt plus a device-side launch of the
     // exact sweep (~0.1 ms), so after a failure the next `backoff` calls go to the exact sweep directly

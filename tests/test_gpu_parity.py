@@ -650,9 +650,13 @@ def _resident_detok(torch, strat, toks: np.ndarray):
     return d_out[:n].cpu().numpy()
 
 
-def test_detokenize_vs_oracle(ctx, nat, torch_mod, oracle):
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_detokenize_vs_oracle(nat, torch_mod, oracle, variant, monkeypatch):
     """GPU detokenizer against the oracle's on arbitrary valid token streams, ragged sizes,
-    contiguous ids and ids with holes, device-resident and host entry points."""
+    contiguous ids and ids with holes, device-resident and host entry points; the count/scan/emit form (0, the
+    default) and the fused single pass (1)."""
+    monkeypatch.setenv("BLT_DETOK_VARIANT", variant)
+    ctx = nat.Context(0)
     rng = np.random.default_rng(11)
     tables = {
         "contiguous": {(int(k) & 255, int(k) >> 8): 256 + i for i, k in enumerate(rng.choice(65536, 3000, replace=False))},
@@ -669,8 +673,9 @@ def test_detokenize_vs_oracle(ctx, nat, torch_mod, oracle):
             continue
         om = oracle.Merges(final)
         s = ctx.bpe_from_pairs(final)
-        for n_tok in (0, 1, 2, 7, 8, 9, 255, 256, 257, 4097, 65536, 100001, 1 * MiB + 3, 3 * MiB + 5):
-            for p_wide in (0.0, 0.5, 1.0):
+        for n_tok in (0, 1, 2, 7, 8, 9, 255, 256, 257, 4097, 32767, 32768, 32769, 65536, 100001, 1 * MiB + 3, 3 * MiB + 5,
+                      148 * 32768 * 2 + 11):
+            for p_wide in (0.0, 0.5, 1.0, 0.03, 0.97):
                 wide = rng.random(n_tok) < p_wide
                 toks = np.where(wide, ids[rng.integers(0, len(ids), n_tok)], rng.integers(0, 256, n_tok)).astype(">u2")
                 stream = toks.view(np.uint8)
@@ -685,9 +690,22 @@ def test_detokenize_vs_oracle(ctx, nat, torch_mod, oracle):
     assert np.array_equal(p.detokenize_host(raw[: 2 * (raw.size // 2)]), raw[: 2 * (raw.size // 2)])
 
 
-def test_detokenize_errors_and_prefix(ctx, nat, torch_mod, oracle):
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_detokenize_errors_and_prefix(nat, torch_mod, oracle, variant, monkeypatch):
+    monkeypatch.setenv("BLT_DETOK_VARIANT", variant)
+    ctx = nat.Context(0)
     pairs = {(97, 98): 256, (98, 97): 300}
     s = ctx.bpe_from_pairs(pairs)
+    # an output that is too small, far into a long stream: a capacity error, nothing written behind the capacity
+    torch = torch_mod
+    long_toks = np.tile(np.frombuffer(b"\x01\x00\x00c", dtype=np.uint8), 3 * MiB)      # (a,b), c -> 3 bytes per 2 tokens
+    d_in = torch.from_numpy(long_toks).cuda()
+    cap = 5 * MiB
+    d_out = torch.full((cap + 4096,), 0xEE, dtype=torch.uint8, device="cuda")
+    with pytest.raises(nat.BltError) as e:
+        s.detokenize_resident(d_in.data_ptr(), long_toks.size, d_out.data_ptr(), cap, torch.cuda.current_stream().cuda_stream)
+    assert e.value.code == -7
+    assert bool((d_out[cap:] == 0xEE).all()), "wrote past the capacity"
     ok = np.frombuffer(b"\xff\x01\x01\x00\x00c\x01\x2c", dtype=np.uint8)          # Text prefix, (a,b), c, (b,a)
     assert bytes(s.detokenize_host(ok, has_content_type=True)) == b"abcba"
     for bad in (b"\x00", b"\x01\x01", b"\x01\x00" * 5000 + b"\x01\x2b", b"\xff\x01\x00a"):  # odd, unknown ids (hole, 299), prefix unasked

@@ -69,10 +69,11 @@ def general_map(peak):
 
 
 def detok(peak, n, chunk, iters):
-    """Detokenizer on the token streams of configs 3 (every token a merged id) and 2 (mixed)."""
+    """Detokenizer on the token streams of configs 3 (every token a merged id), 2 (mixed widths) and of
+    the mixed corpus with 32 768 rules (9)."""
     stream = torch.cuda.current_stream().cuda_stream
-    for cfg, rules in ((3, 32768), (2, 256)):
-        data = synth.text(n, synth.SEED_CONFIG[cfg])
+    for cfg, rules in ((3, 32768), (2, 256), (9, 32768)):
+        data = synth.mixed(n, synth.SEED_MIXED) if cfg == 9 else synth.text(n, synth.SEED_CONFIG[cfg])
         l, r = synth.merges_from_sample(data, rules)
         ctx = nat.Context(0)
         strat = ctx.bpe_from_pairs({(int(a), int(b)): 256 + i for i, (a, b) in enumerate(zip(l, r))})
@@ -92,7 +93,7 @@ def detok(peak, n, chunk, iters):
         ms = sorted(a.elapsed_time(b) for a, b in evs)
         med = ms[len(ms) // 2]
         alg = nt + n
-        print(json.dumps({"config": f"detokenize config {cfg} tokens", "token_bytes": nt, "out_bytes": n, "ms_median": round(med, 4),
+        print(json.dumps({"config": f"detokenize config {cfg} tokens", "form": {"0": "count/scan/emit", "1": "fused"}.get(os.environ.get("BLT_DETOK_VARIANT", "0"), "?"), "token_bytes": nt, "out_bytes": n, "ms_median": round(med, 4),
                           "ms_best": round(ms[0], 4), "output_GBps": round(n / med / 1e6, 1), "algorithmic_GBps": round(alg / med / 1e6, 1),
                           "frac_of_measured_hbm": round(alg / med / 1e6 / peak, 4)}), flush=True)
         strat.close()
