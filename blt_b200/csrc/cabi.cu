@@ -241,7 +241,7 @@ int decode_ctrl(const uint64_t *h_ctrl, DeviceResult *res) {
     if (overflow == 3u) return fail(BLT_ERR_CUDA, "a single-pass kernel timed out waiting for a tile (look-back or bulk copy)");
     if (overflow) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
     if (res->owner) {  // the dense pass was attempted: tell the predictor how it went
-        res->owner->dense_feedback(reinterpret_cast<const uint32_t *>(h_ctrl)[5] != 0u);
+        res->owner->dense_feedback(reinterpret_cast<const uint32_t *>(h_ctrl)[5] != 0u, reinterpret_cast<const uint32_t *>(h_ctrl)[7]);
         res->owner = nullptr;
     }
     if (res->len_scale == 1 && reinterpret_cast<const uint32_t *>(h_ctrl)[6] != 0u)
@@ -317,8 +317,10 @@ bool blt_strategy::want_dense() {
     dense_skip.store(dense_backoff.load(std::memory_order_relaxed), std::memory_order_relaxed);
     return true;
 }
-void blt_strategy::dense_feedback(bool failed) {
-    if (!failed) { dense_backoff.store(0, std::memory_order_relaxed); dense_skip.store(0, std::memory_order_relaxed); return; }
+void blt_strategy::dense_feedback(bool failed, uint32_t prefix_permille) {
+    // A failed attempt keeps the dense output of the chunks in front of the first failed one and hands only the rest to
+    // the exact sweep, so an attempt that got through a good part of the launch was worth it: keep attempting.
+    if (!failed || prefix_permille >= 250u) { dense_backoff.store(0, std::memory_order_relaxed); dense_skip.store(0, std::memory_order_relaxed); return; }
     const uint32_t b = dense_backoff.load(std::memory_order_relaxed);
     const uint32_t nb = b ? std::min(2 * b, 1024u) : 16u;
     dense_backoff.store(nb, std::memory_order_relaxed);

@@ -396,8 +396,8 @@ __device__ __forceinline__ bool fz_chain_poll(const SweepArgs &a, FusedShared *g
     if (lane == 0) {
         st_desc(desc + cur, FZ_P | (c_out ? FZ_P_CARRY : 0ull) | total);
         if (cur == n_tiles - 1) {
-            *a.scratch.total_tokens = total;
-            *a.scratch.merged_any = (total < a.n) ? 1u : 0u;
+            *a.scratch.total_tokens = total + a.total_bias;
+            *a.scratch.merged_any = (total < a.n || a.total_bias != 0) ? 1u : 0u;
             if (a.out_base_tokens + total > a.out_cap_tokens) *a.scratch.overflow = 1u;
         }
     }

@@ -332,8 +332,11 @@ __device__ __forceinline__ Walls<SEG> seg_walls(const SweepArgs &a, const TileIn
 // output is the looked-up id of every even pair, token k of the launch sits at out[k], and no carry
 // or count has to cross a tile.  With an even chunk size no such pair straddles a wall.  The kernel
 // streams under that hypothesis - 16 bytes in, 8 lookups, 16 bytes out per lane, no barrier, no
-// look-back - and raises `abort` at the first pair that is not a rule.  The last CTA to finish then either
-// publishes the totals or launches the exact sweep (sweep3.cuh) from the device, which redoes the launch.
+// look-back - and records the work unit of a pair that is not a rule in the abort word (the smallest such unit
+// wins).  Units in front of the failed unit's chunk are still completed, the ones from that chunk on are given up.
+// The last CTA to finish then either publishes the totals or launches the exact sweep (sweep3.cuh) from the device
+// for the REST of the launch, from the first failed chunk on (the chunks in front of it are dense: their output
+// and chunk ends stand, and the sweep's total is biased by their tokens).
 // ================================================================================================
 __global__ void __launch_bounds__(kCtaThreads, 1)
 dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int variant, unsigned exact_grid) {
@@ -361,6 +364,15 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
     const int lane = threadIdx.x & 31;
     const uint32_t n_static = gridDim.x * (kCtaThreads / 32);
     bool bad = false;
+    // The abort word holds ~unit of the smallest failed unit (0: none; atomicMax).  When the chunk size is a whole number
+    // of units, a failure only stops the units from the first unit of the failed unit's chunk on (`floor`).
+    const unsigned long long ck = (a.chunk == 0 || a.chunk > n) ? n : a.chunk;
+    const uint32_t units_per_chunk = (ck % (kDenseUnitSegs * 16ull) == 0 && ck / (kDenseUnitSegs * 16ull) < 0x7fffffffull)
+                                         ? uint32_t(ck / (kDenseUnitSegs * 16ull)) : 0u;  // 0: any failure stops everything
+    auto floor_of = [&](uint32_t word) -> uint32_t {  // the first unit that is given up
+        if (word == 0u) return 0xffffffffu;
+        return units_per_chunk ? (~word / units_per_chunk) * units_per_chunk : 0u;
+    };
     uint32_t ab = 0;       // the abort word as it was one trip ago: never waited for inside a trip
     uint32_t nxt_raw = 0;  // lane 0: the unit after the current one (fetched one unit ahead)
     if (lane == 0) nxt_raw = atomicAdd(work_counter, 1u) + n_static;
@@ -376,8 +388,9 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
 #pragma unroll
         for (int u = 0; u < U; ++u) w[u] = ldg_stream_v4(in + (s0 + u * 32) * 16);
     };
-    // looks up and stores one trip; true = this warp or somebody else gave up
-    auto work = [&](const uint4 *w, unsigned long long s0) {
+    // looks up and stores one trip of unit `unit`; true = this warp gives up (the unit failed, or a unit of its chunk or
+    // of a chunk in front of it has)
+    auto work = [&](const uint4 *w, unsigned long long s0, uint32_t unit) {
         const uint32_t ab_now = ab;
         if (lane == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(abort_flag) : "memory");
 #pragma unroll
@@ -387,7 +400,11 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
             bad = bad || !PairsFE::all_present(v);
             stg_stream_v4(out + (s0 + u * 32) * 8, make_uint4(v[0], v[1], v[2], v[3]));
         }
-        return __any_sync(FULL, bad || ab_now != 0) != 0;
+        if (__any_sync(FULL, bad)) {
+            if (lane == 0) atomicMax(abort_flag, ~unit);
+            return true;
+        }
+        return unit >= floor_of(__shfl_sync(FULL, ab_now, 0));
     };
     uint4 wa[U], wb[U];
     Pos pa{blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5), 0}, pb{0, 0};
@@ -397,11 +414,11 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
         pb = advance(pa);
         const bool next = pb.unit < full_units;
         if (next) load(wb, seg_of(pb));
-        if (work(wa, seg_of(pa)) || !next) break;
+        if (work(wa, seg_of(pa), pa.unit) || !next) break;
         pa = advance(pb);
         more = pa.unit < full_units;
         if (more) load(wa, seg_of(pa));
-        if (work(wb, seg_of(pb))) break;
+        if (work(wb, seg_of(pb), pb.unit)) break;
     }
     // the segments behind the last full unit (fewer than kDenseUnitSegs)
     if (blockIdx.x == gridDim.x - 1 && !bad) {
@@ -423,11 +440,12 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
         }
         if (i < n) out[i / 2] = uint16_t(uint32_t(in[i]) << 8);  // odd length: the last element stays a raw token
     }
-    // one store per CTA: 150 000 threads storing to one word serialise in L2 for tens of microseconds
+    // (a warp that failed inside a unit has recorded the unit already; what is left is the two tails, which belong to
+    // the last chunk: one atomic per CTA - 150 000 threads storing to one word serialise in L2 for tens of microseconds)
     __shared__ uint32_t s_last;
     const bool cta_bad = __syncthreads_or(bad) != 0;
     if (threadIdx.x == 0) {
-        if (cta_bad) *reinterpret_cast<volatile uint32_t *>(abort_flag) = 1u;
+        if (cta_bad) atomicMax(abort_flag, ~full_units);
         __threadfence();
         s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
@@ -435,7 +453,10 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
     if (s_last == 0) return;
     // ---- the last CTA to finish: everybody else's stores (output and abort word) are visible ----
     __threadfence();
-    const bool failed = *reinterpret_cast<volatile uint32_t *>(abort_flag) != 0u;
+    const uint32_t ab_word = *reinterpret_cast<volatile uint32_t *>(abort_flag);
+    const bool failed = ab_word != 0u;
+    const unsigned long long c = (a.chunk == 0 || a.chunk > n) ? n : a.chunk;
+    const unsigned long long n_chunks = (n + c - 1) / c;
     if (!failed) {  // the speculation held: the output is complete, publish the totals of the sweep
         const unsigned long long tokens = (n + 1) / 2;
         if (threadIdx.x == 0) {
@@ -445,23 +466,36 @@ dense_pairs_kernel(const SweepArgs a, const uint16_t *__restrict__ table, int va
             reinterpret_cast<uint32_t *>(a.scratch.ctrl)[5] = 0u;  // "dense pass failed" (read by the host's predictor)
         }
         if (a.chunk_ends != nullptr) {
-            const unsigned long long c = (a.chunk == 0 || a.chunk > n) ? n : a.chunk;
-            const unsigned long long n_chunks = (n + c - 1) / c;
             for (unsigned long long k = threadIdx.x; k < n_chunks; k += blockDim.x)
                 a.chunk_ends[k] = a.chunk_ends_base + ((k + 1 == n_chunks) ? 2 * tokens : (k + 1) * c);
         }
     } else {
-        // Some even pair is not a rule: the exact sweep redoes the launch.  It is enqueued from here (tail
-        // launch: it starts when this grid has completed) so that the host never enqueues - and the GPU never
-        // schedules - three kernels that would have nothing to do in the common case.
+        // Some even pair is not a rule: the exact sweep redoes the launch from the first failed chunk on.  It is enqueued
+        // from here (tail launch: it starts when this grid has completed) so that the host never enqueues - and the GPU
+        // never schedules - three kernels that would have nothing to do in the common case.
+        // Every unit in front of chunk j was completed without a failure (a unit is only given up when a unit of its own
+        // chunk or of a chunk in front of it has failed, and j is the chunk of the smallest failed unit).
+        unsigned long long j = units_per_chunk ? (unsigned long long)(~ab_word / units_per_chunk) : 0ull;
+        if (j >= n_chunks) j = n_chunks - 1;  // (the tails' pseudo unit)
+        if (a.chunk_ends != nullptr) {
+            for (unsigned long long k = threadIdx.x; k < j; k += blockDim.x) a.chunk_ends[k] = a.chunk_ends_base + (k + 1) * c;
+        }
         if (threadIdx.x < 64) reinterpret_cast<uint32_t *>(a.scratch.ctrl)[threadIdx.x] = 0u;
         __syncthreads();
         if (threadIdx.x == 0) {
             reinterpret_cast<uint32_t *>(a.scratch.ctrl)[5] = 1u;
+            reinterpret_cast<uint32_t *>(a.scratch.ctrl)[7] = uint32_t(j * c * 1000ull / n);  // per mille of the launch the dense prefix covers (predictor)
             __threadfence();
-            const bool ok = (variant == 1)   ? tail_launch_sweep3<PairsFE, 8>(a, p, exact_grid)
-                            : (variant == 2) ? tail_launch_sweep3<PairsFE, 4, true>(a, p, exact_grid)
-                                             : tail_launch_sweep3<PairsFE, 4>(a, p, exact_grid);
+            SweepArgs r = a;  // the rest: chunks j .. (c is a multiple of 8 KiB when j != 0: alignment and parity hold)
+            r.in = in + j * c;
+            r.n = n - j * c;
+            r.out_base_tokens = a.out_base_tokens + j * c / 2;
+            if (a.chunk_ends != nullptr) r.chunk_ends = a.chunk_ends + j;
+            r.chunk_ends_base = a.chunk_ends_base + j * c;
+            r.total_bias = a.total_bias + j * c / 2;
+            const bool ok = (variant == 1)   ? tail_launch_sweep3<PairsFE, 8>(r, p, exact_grid)
+                            : (variant == 2) ? tail_launch_sweep3<PairsFE, 4, true>(r, p, exact_grid)
+                                             : tail_launch_sweep3<PairsFE, 4>(r, p, exact_grid);
             if (!ok) *a.scratch.overflow = 2u;  // reported as a CUDA error by the host (never seen so far)
         }
     }

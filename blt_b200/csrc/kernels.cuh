@@ -74,6 +74,7 @@ struct SweepArgs {
     size_t chunk_ends_base;  // bytes added to every chunk_ends entry (output before this launch)
     uint8_t *meta;           // optional (K2 walk variant): one byte per 16-byte segment written by count, read by emit
     SweepScratch scratch;
+    size_t total_bias;       // tokens added to the published total (the dense pass's prefix when the exact sweep redoes only the rest)
 };
 
 // Detokenizer (detok.cuh): n_tok big-endian u16 tokens -> bytes.

@@ -132,7 +132,7 @@ struct blt_strategy {
     bool variant_forced = false;
     std::atomic<uint32_t> last_ratio_milli{0};  // 1000 * tokens / input bytes of the most recent call, 0: none yet
     bool want_dense();
-    void dense_feedback(bool failed);
+    void dense_feedback(bool failed, uint32_t prefix_permille = 0);
     std::mutex detok_mu;                  // detokenizer table, built on first use
     uint16_t *d_detok = nullptr;          //   65536 x u16 + 2048 x u32 (DetokArgs::table)
     uint32_t detok_limit = 0, detok_holes = 0;

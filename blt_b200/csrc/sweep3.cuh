@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a,
         }
     }
     if (threadIdx.x == kCtaThreads - 1) {
-        *a.scratch.total_tokens = b;
-        *a.scratch.merged_any = (b < a.n) ? 1u : 0u;
+        *a.scratch.total_tokens = b + a.total_bias;
+        *a.scratch.merged_any = (b < a.n || a.total_bias != 0) ? 1u : 0u;
         if (a.out_base_tokens + b > a.out_cap_tokens) *a.scratch.overflow = 1u;
     }
 }

@@ -249,6 +249,37 @@ def test_dense_predictor_sequence(ctx, torch_mod, oracle):
     s.close()
 
 
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+def test_dense_prefix_and_exact_rest(nat, torch_mod, oracle, variant, monkeypatch):
+    """The dense pass fails in some chunk: the chunks in front of it keep their dense output, the exact sweep redoes
+    the rest (device-side launch).  Foreign bytes in the first / a middle / the last chunk, in several chunks, in the
+    ragged tails, with chunk sizes that are and are not a whole number of 8 KiB work units; output and chunk ends are
+    the oracle's."""
+    monkeypatch.setenv("BLT_DENSE", "always")
+    monkeypatch.setenv("BLT_SWEEP_VARIANT", variant)
+    ctx = nat.Context(0)
+    pairs = {(a, b): 256 + 4 * (a - 97) + (b - 97) for a in range(97, 101) for b in range(97, 101)}   # every pair of a..d
+    om = oracle.Merges(pairs)
+    s = ctx.bpe_from_pairs(pairs)
+    rng = np.random.default_rng(23)
+    for n, chunk in ((2 * MiB, 128 * 1024), (2 * MiB + 8192 + 37, 128 * 1024), (3 * MiB + 5, 192 * 1024 + 2), (1 * MiB, 0), (5 * MiB + 9, 1 * MiB)):
+        c = chunk if chunk else n
+        n_chunks = (n + c - 1) // c
+        base = rng.integers(97, 101, size=n, dtype=np.uint8)
+        spots = [[], [0], [n - 1], [n - 2], [c * (n_chunks // 2) + 1000], [c * (n_chunks // 2) + 1001],
+                 [c - 2, c * (n_chunks - 1) + 4], [c * (n_chunks // 3) + 77, c * (n_chunks // 3) + 78, c * (2 * n_chunks // 3) + 12]]
+        for sp in spots:
+            data = base.copy()
+            for q in sp:
+                data[min(q, n - 1)] = 0x20
+            want = oracle.run_buffer("bpe", data, c, 4, om)
+            got, ends = resident(torch_mod, s, data, chunk)
+            assert np.array_equal(got, want), (n, chunk, sp)
+            want_ends = np.cumsum([len(oracle.process_chunk("bpe", data[k * c:(k + 1) * c], om)) for k in range(n_chunks)])
+            assert np.array_equal(ends, want_ends), (n, chunk, sp)
+    s.close()
+
+
 def test_long_runs_and_carry_chains(ctx, torch_mod, oracle):
     """A whole chunk of one byte is a single run: parity must carry across threads, warps, tiles."""
     pairs = {(97, 97): 256, (97, 98): 257, (98, 97): 258, (98, 98): 259}
