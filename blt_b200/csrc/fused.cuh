@@ -165,6 +165,9 @@ constexpr bool kStageSwizzle = true;
 constexpr bool kStageSwizzle = false;  // measured: the swizzle costs 2 instructions per position and does not pay (config 2: 1.39 -> 1.30 ms per GiB without it)
 #endif
 __device__ __forceinline__ uint32_t stage_swz(uint32_t addr) { return kStageSwizzle ? (addr ^ ((addr >> 3) & 0x70u)) : addr; }
+#ifndef BLT_FZ_NO_BULK_FLUSH
+static_assert(!kStageSwizzle, "the bulk-copy flush reads the staging line as it lies");
+#endif
 
 // The SEG/2 pairs of one 16-byte segment that start at positions of parity PAR: the big-endian u16 to emit at each of
 // those positions (merged id if the pair is a rule, else the element itself), two per register in position order.
@@ -607,7 +610,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             FZ_PROF({ const long long t1 = clock64(); pf_copy += t1 - pf_t; pf_t = t1; ++pf_tiles; })
             // ---- count: lookups (retained), run parity under carry_in = 0, the slice's carry function ----
             bool t_id = true;
-            uint32_t t_const = 0, delta = 0, cnt0 = 0;
+            uint32_t t_const = 0, delta = 0, cnt_lane = 0;  // (the lanes' counts are added up once per slice, not per round)
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 const uint32_t round_off = slice_off + uint32_t(k * 512);
@@ -642,7 +645,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 const uint32_t e = valid & ~((st << 1) | cin0);
                 const uint32_t cnt = __popc(e);
                 em[NS][k] = e;
-                cnt0 += __reduce_add_sync(FULL, cnt);
+                cnt_lane += cnt;
                 if (nid) {
                     if (t_id) {  // the slice's first non-identity segment is the only one whose count sees the slice's carry_in
                         const int f = __ffs(nid) - 1;
@@ -654,6 +657,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     t_const = (cob >> (31 - __clz(nid))) & 1u;
                 }
             }
+            const uint32_t cnt0 = __reduce_add_sync(FULL, cnt_lane);
             // every lane has read its share of the buffer: the slice of the next tile may land in it
             const uint32_t nxt_tile = gs->tile_id[(it + 1) % GS];
             if (nxt_tile != 0xffffffffu) fz_warp_copy<C>(a, nxt_tile, wg, slice, wbar, lane);
@@ -777,6 +781,10 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                 // position (no two neighbours are both silent) and is overwritten by it; only position 15, whose
                 // successor belongs to the next lane, is predicated.  Silent positions behind the end of the input pile
                 // up in the scratch slot behind the last token.  (The cursor bump is a multiply-high-add: fma pipe.)
+#ifndef BLT_FZ_NO_BULK_FLUSH
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous tile's bulk copy has read the line
+                __syncwarp();
+#endif
                 uint32_t sp[R];
 #pragma unroll
                 for (int k = 0; k < R; ++k) sp[k] = stage_s + 2u * (head + pos[k]);
@@ -824,6 +832,20 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                         *reinterpret_cast<uint16_t *>(gout + 2u * L) = uint16_t(tv);
                     }
                 }
+#ifndef BLT_FZ_NO_BULK_FLUSH
+                // the whole vectors leave through the bulk-copy unit (shared -> global, one instruction by one lane): no
+                // LDS.128 / STG.128 loop, no wavefronts of the shared-memory load pipe.  The lanes' generic-proxy stores
+                // are fenced towards the async proxy first; the line is not written again before the copy has read it
+                // (wait_group.read at the top of the next compaction).
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && v_end > v_first) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gout + 16u * v_first),
+                                 "r"(stage_s + 16u * v_first), "r"(16u * (v_end - v_first))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+#else
 #pragma unroll 2
                 for (uint32_t v0 = 0; v0 < v_end; v0 += 32u) {  // warp-uniform trip count
                     const uint32_t v = v0 + uint32_t(lane);
@@ -837,6 +859,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     }
                 }
                 __syncwarp();
+#endif
             }
             FZ_PROF({ const long long t1 = clock64(); pf_emit += t1 - pf_t; pf_t = t1; })
         }
@@ -851,6 +874,10 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
             if (!iteration(FzIC<3>{}, FzIC<0>{}, it + 3)) break;
         }
     }
+#ifndef BLT_FZ_NO_BULK_FLUSH
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the CTA's shared memory outlives its bulk copies
+    __syncwarp();
+#endif
     FZ_PROF(if (lane == 0 && blockIdx.x < 256) {
         unsigned long long *pp = g_fz_prof + (size_t(blockIdx.x) * 32 + wg) * 8;
         uint32_t smid;

@@ -47,7 +47,13 @@ while time.time() < t_end:
         p = 1.0 / np.arange(1, alpha + 1); p /= p.sum()
         data = nrng.choice(np.array(syms, dtype=np.uint8), size=n, p=p)
     data = np.ascontiguousarray(data, dtype=np.uint8)
-    density = rng.choice([1.0, 0.95, 0.6, 0.2, 0.02])
+    density = rng.choice([1.0, 1.0, 0.95, 0.6, 0.2, 0.02])
+    if density == 1.0 and alpha < 256 and n and rng.random() < 0.6:
+        # a table that covers every pair of the alphabet and a few foreign bytes: the dense pass holds up to the first
+        # chunk with one of them, the exact sweep redoes the rest
+        foreign = next(b for b in range(256) if b not in syms)
+        for _ in range(rng.choice([1, 1, 2, 5])):
+            data[rng.randrange(n)] = foreign
     allp = [(a, b) for a in syms for b in syms] if alpha <= 26 else [(rng.choice(syms), rng.choice(syms)) for _ in range(20000)]
     rng.shuffle(allp)
     keys = list(dict.fromkeys(allp))[: max(0, int(len(allp) * density))]

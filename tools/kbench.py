@@ -16,6 +16,9 @@ import torch  # noqa: E402
 
 from blt_b200 import _native as nat, synth  # noqa: E402
 
+if os.environ.get("BLT_ALT_LIB"):  # an alternative build of the library (A/B runs on one box)
+    nat.LIB_PATH = os.environ["BLT_ALT_LIB"]
+
 VARIANT_NAMES = ["exact r4", "exact r8", "exact walk", "fused 15x4 d2", "fused 23x2 d2"]
 
 
