@@ -152,7 +152,7 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
             // The loop of tokenizer.rs:63-86 (sweep until one merges nothing), for up to 8 chunks at a time: every chunk
             // of the batch launches its next sweep, ONE host synchronisation reads all their "merged anything" flags
             // and totals, chunks that are done drop out.  (Round 1 synchronised once per sweep and chunk.)
-            const bltk::HashTableView view{s->d_slots, s->hash_mask, s->d_can_left, s->d_can_right};
+            const bltk::HashTableView view{s->d_slots, s->hash_mask, s->d_can_left, s->d_can_right, s->d_pair_bloom, s->d_bytemap};
             const size_t n_chunks = (n + chunk - 1) / chunk;
             size_t batch = std::min<size_t>(n_chunks, 8);
             while (batch > 1 && batch * 5 * chunk > (size_t(2) << 30)) --batch;  // at most 2 GiB of ping-pong buffers
@@ -396,7 +396,7 @@ static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **ou
         size_t cap = 16;
         while (cap < 2 * s->rules.size() + 2) cap <<= 1;
         std::vector<bltk::HashSlot> slots(cap, bltk::HashSlot{0, 0, 0});
-        std::vector<uint32_t> cl(2048, 0), cr(2048, 0);
+        std::vector<uint32_t> cl(2048, 0), cr(2048, 0), bloom(2048, 0);
         for (const auto &r : s->rules) {
             const uint32_t key = (uint32_t(r.left) << 16) | r.right;
             uint32_t h = bltk::hash_pair(key) & uint32_t(cap - 1);
@@ -404,6 +404,8 @@ static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **ou
             slots[h] = bltk::HashSlot{key, r.value, 1};
             cl[r.left >> 5] |= 1u << (r.left & 31);
             cr[r.right >> 5] |= 1u << (r.right & 31);
+            const uint32_t bb = bltk::pair_bloom_bit(r.left, r.right);
+            bloom[bb >> 5] |= 1u << (bb & 31);
         }
         s->hash_mask = uint32_t(cap - 1);
         CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_slots), cap * sizeof(bltk::HashSlot)));
@@ -412,6 +414,19 @@ static int build_strategy(blt_ctx *ctx, blth::MergeList rules, blt_strategy **ou
         CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_can_right), 8192));
         CUDA_TRY(cudaMemcpy(s->d_can_left, cl.data(), 8192, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(s->d_can_right, cr.data(), 8192, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_pair_bloom), 8192));
+        CUDA_TRY(cudaMemcpy(s->d_pair_bloom, bloom.data(), 8192, cudaMemcpyHostToDevice));
+        // the first sweep reads bytes: the rules with byte components as a direct table (values + exact membership bitmap)
+        std::vector<uint16_t> bytemap(bltk::kPairTableEntries + 4096, 0);
+        uint32_t *member = reinterpret_cast<uint32_t *>(bytemap.data() + bltk::kPairTableEntries);
+        for (const auto &r : s->rules) {
+            if (r.left > 255 || r.right > 255) continue;
+            const uint32_t idx = bltk::pair_table_index(r.left, r.right);
+            bytemap[idx] = r.value;  // (the list holds the final map: one rule per key)
+            member[idx >> 5] |= 1u << (idx & 31);
+        }
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_bytemap), bytemap.size() * 2));
+        CUDA_TRY(cudaMemcpy(s->d_bytemap, bytemap.data(), bytemap.size() * 2, cudaMemcpyHostToDevice));
     }
     // tuning / test switches: tile size of the exact sweep, and whether the dense pass runs in front of it
     if (const char *v = getenv("BLT_SWEEP_VARIANT")) { s->variant = atoi(v); s->variant_forced = true; }
@@ -432,6 +447,8 @@ blt_strategy::~blt_strategy() {
     if (d_slots) cudaFree(d_slots);
     if (d_can_left) cudaFree(d_can_left);
     if (d_can_right) cudaFree(d_can_right);
+    if (d_pair_bloom) cudaFree(d_pair_bloom);
+    if (d_bytemap) cudaFree(d_bytemap);
     if (d_detok) cudaFree(d_detok);
     resident.release();
     if (ctx) ctx->release_ref();

@@ -204,16 +204,18 @@ struct PairsFE {
     }
 };
 
-// K3 front end: general HashMap<(u16,u16),u16> in global memory (L2-resident), prefiltered by two
-// 8 KiB shared-memory bitmaps.  Input is raw bytes (first sweep) or big-endian u16 tokens.
+// K3 front end: general HashMap<(u16,u16),u16> in global memory (L2-resident), prefiltered by three
+// 8 KiB shared-memory bitmaps ("can be a left / right component", and a Bloom filter over the pairs, without which
+// the misses among the candidate pairs - most of them on text - each cost dependent global loads).
+// Input is raw bytes (first sweep) or big-endian u16 tokens.
 template <bool IN_U16>
 struct HashFE {
     static constexpr int SEG = IN_U16 ? 8 : 16;
     static constexpr int ELEM = IN_U16 ? 2 : 1;
-    static constexpr int TABLE_BYTES = 2 * 8192;
+    static constexpr int TABLE_BYTES = 3 * 8192;
     static constexpr bool kMembershipInValue = false;  // ids may be < 256 and may equal the element
     struct Params { HashTableView t; };
-    const uint32_t *can_left, *can_right;  // shared memory
+    const uint32_t *can_left, *can_right, *bloom;  // shared memory
     const HashSlot *slots;
     uint32_t mask;
 
@@ -222,9 +224,11 @@ struct HashFE {
         for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
             s[i] = p.t.can_left[i];
             s[2048 + i] = p.t.can_right[i];
+            s[4096 + i] = p.t.pair_bloom[i];
         }
         can_left = s;
         can_right = s + 2048;
+        bloom = s + 4096;
         slots = p.t.slots;
         mask = p.t.mask;
     }
@@ -248,7 +252,8 @@ struct HashFE {
     }
     __device__ __forceinline__ uint32_t lookup_one(uint32_t cur, uint32_t nxt, uint32_t *out) const {
         *out = cur;
-        if (((can_left[cur >> 5] >> (cur & 31)) & (can_right[nxt >> 5] >> (nxt & 31)) & 1u)) {
+        const uint32_t bb = pair_bloom_bit(cur, nxt);
+        if (((can_left[cur >> 5] >> (cur & 31)) & (can_right[nxt >> 5] >> (nxt & 31)) & (bloom[bb >> 5] >> (bb & 31)) & 1u)) {
             const uint32_t key = (cur << 16) | nxt;
             uint32_t h = hash_pair(key) & mask;
             for (;;) {
@@ -268,6 +273,49 @@ struct HashFE {
             const uint32_t nxt = par ? elem(w, next, 2 * i + 2) : elem(w, next, 2 * i + 1);
             uint32_t out;
             present |= lookup_one(cur, nxt, &out) << i;
+            const uint32_t be = __byte_perm(out, 0, 0x4401);
+            if (i & 1) vals[i >> 1] |= be << 16; else vals[i >> 1] = be;
+        }
+        return present;
+    }
+    __device__ __forceinline__ void lookup_vals(const uint4 &, uint32_t, uint32_t, uint32_t *) const {}
+    __device__ __forceinline__ static bool all_present(const uint32_t *) { return false; }
+    __device__ __forceinline__ static uint32_t present_mask(const uint32_t *) { return 0; }
+};
+
+// K3 front end of the FIRST sweep (byte input): only rules whose two components are bytes can match there, and those
+// fit a direct table in shared memory - 65 536 values plus an exact "is a rule" bitmap (a value says nothing about
+// membership here: ids may be < 256 and may equal the element).  No probe of the hash table, no divergence.
+struct ByteMapFE {
+    using H = HashFE<false>;
+    static constexpr int SEG = 16;
+    static constexpr int ELEM = 1;
+    static constexpr int TABLE_BYTES = kPairTableEntries * 2 + 8192;
+    static constexpr bool kMembershipInValue = false;
+    struct Params { const uint16_t *bytemap; };
+    const uint16_t *vals16;   // shared memory
+    const uint32_t *member;
+
+    __device__ __forceinline__ void init(const Params &p, unsigned char *smem) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.bytemap);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = threadIdx.x; i < TABLE_BYTES / 16; i += blockDim.x) dst[i] = src[i];
+        vals16 = reinterpret_cast<const uint16_t *>(smem);
+        member = reinterpret_cast<const uint32_t *>(smem + kPairTableEntries * 2);
+    }
+    __device__ __forceinline__ static uint32_t first_elem(const uint4 &w) { return H::first_elem(w); }
+    __device__ __forceinline__ static uint32_t raw_be(const uint4 &w, int j) { return H::raw_be(w, j); }
+    __device__ __forceinline__ static uint32_t load_elem(const void *in, size_t pos) { return H::load_elem(in, pos); }
+    __device__ __forceinline__ uint32_t lookup_half(const uint4 &w, uint32_t next, uint32_t par, uint32_t *vals) const {
+        uint32_t present = 0;
+#pragma unroll
+        for (int i = 0; i < SEG / 2; ++i) {
+            const uint32_t cur = par ? H::elem(w, next, 2 * i + 1) : H::elem(w, next, 2 * i);
+            const uint32_t nxt = par ? H::elem(w, next, 2 * i + 2) : H::elem(w, next, 2 * i + 1);
+            const uint32_t idx = pair_table_index(cur, nxt);
+            const uint32_t hit = (member[idx >> 5] >> (idx & 31)) & 1u;
+            const uint32_t out = hit ? uint32_t(vals16[idx]) : cur;
+            present |= hit << i;
             const uint32_t be = __byte_perm(out, 0, 0x4401);
             if (i & 1) vals[i >> 1] |= be << 16; else vals[i >> 1] = be;
         }
@@ -635,8 +683,8 @@ cudaError_t launch_bpe_sweep_hash(const SweepArgs &a, const HashTableView &t, bo
         HashFE<true>::Params p{t};
         return launch_sweep3<HashFE<true>, 8>(a, p, stream);
     }
-    HashFE<false>::Params p{t};
-    return launch_sweep3<HashFE<false>, 4>(a, p, stream);
+    ByteMapFE::Params p{t.bytemap};
+    return launch_sweep3<ByteMapFE, 4>(a, p, stream);
 }
 
 }  // namespace bltk

@@ -36,11 +36,20 @@ __host__ __device__ inline uint32_t hash_pair(uint32_t key) {
     key ^= key >> 15; key *= 0x2c1b3c6du; key ^= key >> 12; key *= 0x297a2d39u; key ^= key >> 15;
     return key;
 }
+// One-hash Bloom filter over the keys (65 536 bits): a pair whose bit is clear is not a rule, so the table in global
+// memory is only probed for rules and for a share of n_rules / 65 536 of the other candidate pairs.
+__host__ __device__ inline uint32_t pair_bloom_bit(uint32_t left, uint32_t right) {
+    const uint32_t h = left * 40503u + right * 60493u;
+    return (h ^ (h >> 15)) & 0xFFFFu;
+}
 struct HashTableView {
     const HashSlot *slots;     // device
     uint32_t mask;             // capacity - 1 (capacity is a power of two, load <= 0.5)
     const uint32_t *can_left;  // device bitmap, 65 536 bits: token appears as a left component
     const uint32_t *can_right; // device bitmap, 65 536 bits: token appears as a right component
+    const uint32_t *pair_bloom; // device bitmap, 65 536 bits: pair_bloom_bit(left, right) of every key
+    const uint16_t *bytemap;   // device: the rules whose two components are bytes, direct-indexed by pair_table_index:
+                               // 65 536 values (host order), then a 65 536-bit "is a rule" bitmap (first sweep: byte input)
 };
 
 // Per-launch scratch in device memory (the control block is zeroed by the launcher before every sweep).

@@ -116,7 +116,8 @@ struct blt_strategy {
     blth::MergeList rules;
     uint16_t *d_table = nullptr;          // K2 byte-pair table
     bltk::HashSlot *d_slots = nullptr;    // K3 hash table
-    uint32_t *d_can_left = nullptr, *d_can_right = nullptr;
+    uint32_t *d_can_left = nullptr, *d_can_right = nullptr, *d_pair_bloom = nullptr;
+    uint16_t *d_bytemap = nullptr;        // K3, first sweep: direct table of the rules with byte components
     uint32_t hash_mask = 0;
     int variant = 3;                      // K2 exact sweep: 3 = fused single pass (default), 0/1/2 = count/scan/emit forms, 4 = fused 23x2
     int detok_variant = 0;                // detokenizer: 0 = count/scan/emit (default, measured faster), 1 = fused single pass (BLT_DETOK_VARIANT)
