@@ -185,6 +185,7 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
                         a.out_cap_tokens = chunk; a.out_base_tokens = 0;
                         a.chunk_ends = nullptr; a.chunk_ends_base = 0;
                         a.scratch = ln.scratch;
+                        a.skip_unmerged_emit = live[j].u16 ? 1u : 0u;
                         CUDA_TRY(bltk::launch_bpe_sweep_hash(a, view, live[j].u16, stream));
                         CUDA_TRY(cudaMemcpyAsync(ln.h_ctrl, ln.scratch.ctrl, 32, cudaMemcpyDeviceToHost, stream));
                         ++res->launches;
@@ -198,10 +199,14 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
                         const uint64_t total = ln.h_ctrl[0];
                         const uint32_t merged = reinterpret_cast<const uint32_t *>(ln.h_ctrl)[3];
                         if (reinterpret_cast<const uint32_t *>(ln.h_ctrl)[4]) return fail(BLT_ERR_CAPACITY, "output capacity exceeded");
-                        live[j].cur = ln.d_work[live[j].which];
-                        live[j].n = size_t(total);
-                        live[j].u16 = true;
-                        live[j].which ^= 1;
+                        // a sweep over tokens that merges nothing writes nothing (skip_unmerged_emit): its input is the
+                        // result; the first sweep always writes, it widens the bytes
+                        if (merged || !live[j].u16) {
+                            live[j].cur = ln.d_work[live[j].which];
+                            live[j].n = size_t(total);
+                            live[j].u16 = true;
+                            live[j].which ^= 1;
+                        }
                         if (!merged) live[j].active = false;  // tokenizer.rs:83-85
                         else any = true;
                     }

@@ -84,6 +84,7 @@ struct SweepArgs {
     uint8_t *meta;           // optional (K2 walk variant): one byte per 16-byte segment written by count, read by emit
     SweepScratch scratch;
     size_t total_bias;       // tokens added to the published total (the dense pass's prefix when the exact sweep redoes only the rest)
+    uint32_t skip_unmerged_emit;  // K3: a sweep that merges nothing writes nothing (its output would equal its input; the host keeps the input)
 };
 
 // Detokenizer (detok.cuh): n_tok big-endian u16 tokens -> bytes.

@@ -346,6 +346,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a,
     constexpr int HV = C::HV;
     constexpr uint32_t ALL = C::ALL;
     extern __shared__ __align__(16) unsigned char smem[];
+    // the verifying sweep of a general map (tokenizer.rs:83-85): the scan found that nothing merges
+    if (a.skip_unmerged_emit && *reinterpret_cast<const volatile uint32_t *>(a.scratch.merged_any) == 0u) return;
     FE fe;
     fe.init(fp, smem);
     __syncthreads();
