@@ -68,6 +68,7 @@ void Workspace::release_lanes() {
     lane_chunk = 0;
 }
 int Workspace::ensure_lanes(size_t chunk_bytes, size_t n_lanes) {
+    if (!h_batch) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_batch), 8 * sizeof(bltk::SweepArgs), cudaHostAllocMapped));
     if (chunk_bytes > lane_chunk) release_lanes();
     lane_chunk = std::max(lane_chunk, chunk_bytes);
     while (lanes.size() < n_lanes) {
@@ -89,6 +90,8 @@ void Workspace::release() {
     for (auto &p : d_work) if (p) cudaFree(p);
     if (d_align) cudaFree(d_align);
     if (h_ctrl) cudaFreeHost(h_ctrl);
+    if (h_batch) cudaFreeHost(h_batch);
+    h_batch = nullptr;
     d_scratch = nullptr; d_work[0] = d_work[1] = nullptr; d_align = nullptr; h_ctrl = nullptr;
     scratch_elems = 0; work_chunk = 0;
 }
@@ -176,6 +179,12 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
                     live[j] = Live{src, len, false, true, 0, 0};
                 }
                 for (bool any = true; any;) {
+                    // one level: the next sweep of every chunk that is still merging, as ONE batch of three launches (the
+                    // chunks of a level read the same kind of input: bytes in the first sweep, tokens afterwards)
+                    bltk::SweepArgs *d_batch = nullptr;
+                    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_batch), ws.h_batch, 0));
+                    int n_act = 0;
+                    bool u16 = false;
                     for (size_t j = 0; j < nb; ++j) {
                         if (!live[j].active) continue;
                         Workspace::GenLane &ln = ws.lanes[j];
@@ -186,7 +195,13 @@ int run_device(blt_strategy *s, Workspace &ws, const uint8_t *d_in, size_t n, si
                         a.chunk_ends = nullptr; a.chunk_ends_base = 0;
                         a.scratch = ln.scratch;
                         a.skip_unmerged_emit = live[j].u16 ? 1u : 0u;
-                        CUDA_TRY(bltk::launch_bpe_sweep_hash(a, view, live[j].u16, stream));
+                        u16 = live[j].u16;
+                        ws.h_batch[n_act++] = a;
+                    }
+                    CUDA_TRY(bltk::launch_bpe_sweep_hash_batch(ws.h_batch, d_batch, n_act, view, u16, stream));
+                    for (size_t j = 0; j < nb; ++j) {
+                        if (!live[j].active) continue;
+                        Workspace::GenLane &ln = ws.lanes[j];
                         CUDA_TRY(cudaMemcpyAsync(ln.h_ctrl, ln.scratch.ctrl, 32, cudaMemcpyDeviceToHost, stream));
                         ++res->launches;
                     }

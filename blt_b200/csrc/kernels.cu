@@ -678,6 +678,16 @@ cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, 
     }
 }
 
+cudaError_t launch_bpe_sweep_hash_batch(const SweepArgs *h_args, const SweepArgs *d_args, int nb, const HashTableView &t, bool in_is_u16,
+                                        cudaStream_t stream) {
+    if (in_is_u16) {
+        HashFE<true>::Params p{t};
+        return launch_sweep3_batch<HashFE<true>, 8>(h_args, d_args, nb, p, stream);
+    }
+    ByteMapFE::Params p{t.bytemap};
+    return launch_sweep3_batch<ByteMapFE, 4>(h_args, d_args, nb, p, stream);
+}
+
 cudaError_t launch_bpe_sweep_hash(const SweepArgs &a, const HashTableView &t, bool in_is_u16, cudaStream_t stream) {
     if (in_is_u16) {
         HashFE<true>::Params p{t};

@@ -118,6 +118,9 @@ cudaError_t launch_fill_chunk_ends(uint64_t *d_ends, size_t n, size_t chunk, uns
 cudaError_t launch_bpe_sweep_pairs(const SweepArgs &a, const uint16_t *d_table, int variant, bool try_dense,
                                    cudaStream_t stream, int *host_launches = nullptr);
 // K3.  in_is_u16: input is BE u16 tokens (true) or raw bytes (false).
+// nb independent sweeps of one input kind in three launches; d_args = device-readable view of h_args (page-locked host memory)
+cudaError_t launch_bpe_sweep_hash_batch(const SweepArgs *h_args, const SweepArgs *d_args, int nb, const HashTableView &t, bool in_is_u16,
+                                        cudaStream_t stream);
 cudaError_t launch_bpe_sweep_hash(const SweepArgs &a, const HashTableView &t, bool in_is_u16,
                                   cudaStream_t stream);
 // Kernels the HOST enqueues per K2 call: the dense pass alone when it is attempted (it launches count, scan

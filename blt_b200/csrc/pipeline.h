@@ -39,6 +39,7 @@ struct Workspace {
     };
     std::vector<GenLane> lanes;
     size_t lane_chunk = 0;
+    bltk::SweepArgs *h_batch = nullptr;       // page-locked, device-readable: the arguments of the sweeps of one level (<= 8)
     int ensure_scratch(size_t n_elems);
     int ensure_work(size_t chunk_bytes);
     int ensure_lanes(size_t chunk_bytes, size_t n_lanes);

@@ -156,7 +156,8 @@ __device__ __forceinline__ uint32_t segment_full(const FE &fe, const SweepArgs &
 constexpr int kMaxRanges = 8192;  // warps of one launch (148 SMs x 32 warps = 4736)
 
 template <class FE, int R>
-__global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a, const typename FE::Params fp) {
+__global__ void __launch_bounds__(kCtaThreads, 1) count_kernel(const SweepArgs a0, const typename FE::Params fp, const SweepArgs *batch) {
+    const SweepArgs a = batch ? batch[blockIdx.y] : a0;  // (a batch: one sweep per blockIdx.y, general maps)
     using C = Sweep3Cfg<FE, R>;
     constexpr int SEG = C::SEG;
     constexpr uint32_t ALL = C::ALL;
@@ -258,7 +259,8 @@ __device__ __forceinline__ ScanFn scan_shfl_up(const ScanFn &f, int d) {
 constexpr int kScanItems = kMaxRanges / kCtaThreads;  // ranges per thread
 
 // One CTA.  tile_status[w] = (carry entering warp w's range) << 63 | tokens emitted by ranges 0..w-1.
-__global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a, int n_ranges) {
+__global__ void __launch_bounds__(kCtaThreads, 1) scan_kernel(const SweepArgs a0, int n_ranges, const SweepArgs *batch) {
+    const SweepArgs a = batch ? batch[blockIdx.y] : a0;
     __shared__ ScanFn warp_agg[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int t0 = threadIdx.x * kScanItems;
@@ -340,7 +342,8 @@ __device__ __forceinline__ void walk_step(uint32_t &sp, uint32_t &standing, uint
 }
 
 template <class FE, int R, bool WALK = false>
-__global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a, const typename FE::Params fp) {
+__global__ void __launch_bounds__(kCtaThreads, 1) emit_kernel(const SweepArgs a0, const typename FE::Params fp, const SweepArgs *batch) {
+    const SweepArgs a = batch ? batch[blockIdx.y] : a0;
     using C = Sweep3Cfg<FE, R>;
     constexpr int SEG = C::SEG;
     constexpr int HV = C::HV;
@@ -624,9 +627,37 @@ cudaError_t launch_sweep3(const SweepArgs &a_in, const typename FE::Params &fp, 
     err = cudaMemsetAsync(a.scratch.ctrl, 0, 256, stream);
     if (err != cudaSuccess) return err;
     const unsigned grid = L::grid_for(a.n, dev);
-    count_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_count, stream>>>(a, fp);
-    scan_kernel<<<1, kCtaThreads, 0, stream>>>(a, int(grid * (kCtaThreads / 32)));
-    emit_kernel<FE, R, WALK><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, stream>>>(a, fp);
+    count_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_count, stream>>>(a, fp, nullptr);
+    scan_kernel<<<1, kCtaThreads, 0, stream>>>(a, int(grid * (kCtaThreads / 32)), nullptr);
+    emit_kernel<FE, R, WALK><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, stream>>>(a, fp, nullptr);
+    return cudaGetLastError();
+}
+
+// A batch of independent sweeps (the chunks of a general map's sweep level) in three launches: blockIdx.y picks the
+// sweep, whose arguments are read from `d_args` (device-readable, e.g. page-locked host memory; `h_args` is the host's
+// view of the same array).  The front-end tables are loaded once per CTA for 1/grid.x of a sweep instead of once per
+// CTA and chunk, and a level costs three launches instead of three per chunk.
+template <class FE, int R>
+cudaError_t launch_sweep3_batch(const SweepArgs *h_args, const SweepArgs *d_args, int nb, const typename FE::Params &fp, cudaStream_t stream) {
+    using L = Sweep3Launch<FE, R, false>;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    err = L::configure(dev);
+    if (err != cudaSuccess) return err;
+    size_t n_max = 0;
+    for (int j = 0; j < nb; ++j) {
+        if (h_args[j].scratch.max_tiles < size_t(2 * kMaxRanges) || h_args[j].meta != nullptr) return cudaErrorInvalidValue;
+        err = cudaMemsetAsync(h_args[j].scratch.ctrl, 0, 256, stream);
+        if (err != cudaSuccess) return err;
+        n_max = std::max(n_max, h_args[j].n);
+    }
+    unsigned grid = L::grid_for(n_max, dev);
+    const unsigned share = std::max(1u, unsigned(sm_count(dev)) / unsigned(nb));  // about one CTA per SM over the whole batch
+    if (grid > share) grid = share;
+    count_kernel<FE, R><<<dim3(grid, nb), dim3(kCtaThreads), L::smem_count, stream>>>(h_args[0], fp, d_args);
+    scan_kernel<<<dim3(1, nb), kCtaThreads, 0, stream>>>(h_args[0], int(grid * (kCtaThreads / 32)), d_args);
+    emit_kernel<FE, R, false><<<dim3(grid, nb), dim3(kCtaThreads), L::smem_emit, stream>>>(h_args[0], fp, d_args);
     return cudaGetLastError();
 }
 
@@ -638,8 +669,8 @@ __device__ bool tail_launch_sweep3(const SweepArgs &a_in, const typename FE::Par
     using L = Sweep3Launch<FE, R, WALK>;
     SweepArgs a = a_in;
     a.meta = WALK ? a.scratch.meta : nullptr;
-    count_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_count, cudaStreamTailLaunch>>>(a, fp);
-    scan_kernel<<<1, kCtaThreads, 0, cudaStreamTailLaunch>>>(a, int(grid * (kCtaThreads / 32)));
-    emit_kernel<FE, R, WALK><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, cudaStreamTailLaunch>>>(a, fp);
+    count_kernel<FE, R><<<dim3(grid), dim3(kCtaThreads), L::smem_count, cudaStreamTailLaunch>>>(a, fp, nullptr);
+    scan_kernel<<<1, kCtaThreads, 0, cudaStreamTailLaunch>>>(a, int(grid * (kCtaThreads / 32)), nullptr);
+    emit_kernel<FE, R, WALK><<<dim3(grid), dim3(kCtaThreads), L::smem_emit, cudaStreamTailLaunch>>>(a, fp, nullptr);
     return cudaGetLastError() == cudaSuccess;
 }
