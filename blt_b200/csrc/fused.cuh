@@ -21,8 +21,8 @@
 //           count is cnt0 - (delta & carry_in), and one warp-wide add gives the offset.  The window spans more than
 //           one round of the deal, so nothing propagates hop by hop inside a round;
 //   emit    (one tile behind) every worker compacts the retained tokens of its whole slice into a warp-private
-//           staging line with unpredicated 2-byte stores (a silent position's token is overwritten by the lane's next
-//           emitting one; the R rounds are R independent store chains) and streams whole 16-byte vectors out.  Only
+//           staging line with 2-byte stores predicated by the emit mask (the R rounds are R independent store chains)
+//           and sends the whole 16-byte vectors out with one bulk copy shared -> global.  Only
 //           the lanes in front of the slice's first non-identity segment depend on the carry_in; they are redone when
 //           it is 1.  A slice that emits exactly one parity everywhere goes out straight from the registers.
 //
@@ -776,11 +776,12 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     stg_stream_v4(a.out + abs0 + size_t(k) * 256 + size_t(lane) * 8, make_uint4(tv[0], tv[1], tv[2], tv[3]));
                 }
             } else if (fits) {
-                // R independent chains of 2-byte stores (position-major so that they interleave).  The stores are NOT
+                // R independent chains of 2-byte stores (position-major so that they interleave), store and cursor bump
+                // under the predicate "this position emits" (default).  -DBLT_FZ_UNPRED_STS: the stores are NOT
                 // predicated: the token of a position that emits nothing lands in the slot of the lane's next emitting
                 // position (no two neighbours are both silent) and is overwritten by it; only position 15, whose
-                // successor belongs to the next lane, is predicated.  Silent positions behind the end of the input pile
-                // up in the scratch slot behind the last token.  (The cursor bump is a multiply-high-add: fma pipe.)
+                // successor belongs to the next lane, is predicated; silent positions behind the end of the input pile
+                // up in the scratch slot behind the last token (measured slower: more lanes per store, more conflicts).
 #ifndef BLT_FZ_NO_BULK_FLUSH
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous tile's bulk copy has read the line
                 __syncwarp();
@@ -803,6 +804,20 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                                 "xor.b32 %0, t, %1;\n\t}"
                                 : "=r"(phys)
                                 : "r"(sp[k]));
+#ifndef BLT_FZ_UNPRED_STS
+                        if (j < 15 && !kStageSwizzle) {
+                            // store and cursor bump under one predicate made by the mask test itself (the same three
+                            // instructions as the unpredicated chain; fewer lanes per store, fewer bank conflicts)
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.u32 p, %2, 0;\n\t"
+                                "@p st.shared.u16 [%0], %1;\n\t"
+                                "@p add.u32 %0, %0, 2;\n\t}"
+                                : "+r"(sp[k])
+                                : "h"(uint16_t(tok)), "r"(bit)
+                                : "memory");
+                        } else
+#endif
                         if (j < 15) {
                             asm volatile("st.shared.u16 [%0], %1;" ::"r"(phys), "h"(uint16_t(tok)) : "memory");
                             if (j == 0) asm("mad.lo.u32 %0, %1, 2, %0;" : "+r"(sp[k]) : "r"(bit));
