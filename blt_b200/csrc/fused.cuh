@@ -119,9 +119,6 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity), "r"(uint32_t(HINT_NS))
             : "memory");
         if (ok != 0u) return true;
-#ifdef BLT_FZ_WAIT_SLEEP
-        __nanosleep(BLT_FZ_WAIT_SLEEP);  // experiment: back off between two looks (the suspended wait wakes up every few tens of cycles)
-#endif
     }
     return false;
 }
