@@ -881,29 +881,29 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
         return true;
     };
 
-#ifdef BLT_FZ_ONE_BODY
-    // experiment: ONE copy of the tile body (count into set 1, emit from set 0, then move set 1 to set 0) instead of D
-    // copies with the roles of the register sets swapped: half the code for the instruction caches, 36 moves per tile
-    static_assert(D == 2, "one-body form");
-    for (uint32_t it = 0;; ++it) {
-        if (!iteration(FzIC<1>{}, FzIC<0>{}, it)) break;
+    if constexpr (D == 2) {
+        // ONE copy of the tile body - count into set 1, emit from set 0, then move set 1 to set 0 (36 register moves per
+        // tile) - instead of D copies with the roles of the register sets swapped: 5 064 instead of 8 024 instructions,
+        // measured 1 % faster (instruction caches)
+        for (uint32_t it = 0;; ++it) {
+            if (!iteration(FzIC<1>{}, FzIC<0>{}, it)) break;
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
+            for (int k = 0; k < R; ++k) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { hv[0][k][q] = hv[1][k][q]; ov[0][k][q] = ov[1][k][q]; }
-            em[0][k] = em[1][k];
+                for (int q = 0; q < 4; ++q) { hv[0][k][q] = hv[1][k][q]; ov[0][k][q] = ov[1][k][q]; }
+                em[0][k] = em[1][k];
+            }
+        }
+    } else {
+        for (uint32_t it = 0;; it += uint32_t(D)) {
+            if (!iteration(FzIC<0>{}, FzIC<1 % D>{}, it)) break;
+            if (!iteration(FzIC<1>{}, FzIC<2 % D>{}, it + 1)) break;
+            if constexpr (D == 4) {
+                if (!iteration(FzIC<2>{}, FzIC<3>{}, it + 2)) break;
+                if (!iteration(FzIC<3>{}, FzIC<0>{}, it + 3)) break;
+            }
         }
     }
-#else
-    for (uint32_t it = 0;; it += uint32_t(D)) {
-        if (!iteration(FzIC<0>{}, FzIC<1 % D>{}, it)) break;
-        if (!iteration(FzIC<1>{}, FzIC<2 % D>{}, it + 1)) break;
-        if constexpr (D == 4) {
-            if (!iteration(FzIC<2>{}, FzIC<3>{}, it + 2)) break;
-            if (!iteration(FzIC<3>{}, FzIC<0>{}, it + 3)) break;
-        }
-    }
-#endif
 #ifndef BLT_FZ_NO_BULK_FLUSH
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the CTA's shared memory outlives its bulk copies
     __syncwarp();
