@@ -565,7 +565,7 @@ fused_sweep_kernel(const SweepArgs a, const uint16_t *__restrict__ table, unsign
                     *a.scratch.overflow = 3u;
                     break;
                 }
-                __nanosleep(20);
+                __nanosleep(20);  // (0 and 150 ns measured: the same time)
             } else {
                 idle = 0;
             }
